@@ -1,0 +1,324 @@
+/*
+ * roadsurf_b200.h -- C ABI of the B200-native RoadSurf per-point simulation loop.
+ *
+ * This header is the drop-in boundary.  Part 1 restates the five Bind(C) interop types of the
+ * reference library and its single C entry point `runsimulation`; a C++ (or Fortran
+ * ISO_C_BINDING) main program that was linked against the reference keeps compiling and running
+ * when linked against libroadsurf_b200.so instead.  Part 2 adds the batched and the
+ * device-resident entry points that make a GPU behind that boundary worthwhile.
+ *
+ * Reference interfaces replaced (paths relative to the fmidev/RoadSurf tree):
+ *   InputPointers    src/InputPointers.f90.inc:4-27      examples/example1/src/InputPointers.h:7-30
+ *   OutputPointers   src/OutputPointers.f90.inc:4-17     examples/example1/src/OutputPointers.h
+ *   InputSettings    src/InputSettings.f90.inc:4-18      examples/example1/src/InputSettings.h:9-27
+ *   InputParameters  src/InputParameters.f90.inc:4-91    examples/example1/src/InputParameters.h:11-110
+ *   LocalParameters  src/LocalParameters.f90.inc:4-15    examples/example1/src/LocalParameters.h:11-30
+ *   runsimulation    examples/example1/src/Simulation.f90:4-6 (BIND(C), lower-case symbol)
+ *                    examples/example1/src/roadrunner.cpp:22-29 (C++ declaration)
+ *
+ * No torch / CUDA types appear in any signature: plain pointers, ints and doubles only.
+ */
+#ifndef ROADSURF_B200_H
+#define ROADSURF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* Part 1: the reference ABI                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+
+/* src/InputPointers.f90.inc:4-27.  160 bytes on x86-64 SysV.  Every array has inputLen
+ * elements except local_horizons, which always has 360 (src/ConnectFortran2Carrays.f90:52).
+ * The callee mutates VZ[0], SW_dir[i], and (sky view active) SW[i], SW_dir[i], LW[i] in the
+ * reference; see INTEGRATION.md for what this library does instead. */
+typedef struct InputPointers
+{
+  int inputLen;
+  double* c_tair;           /* air temperature (C) */
+  double* c_tdew;           /* dew point temperature (C) */
+  double* c_VZ;             /* wind speed (m/s) */
+  double* c_Rhz;            /* relative humidity (%) */
+  double* c_prec;           /* precipitation (mm/h) */
+  double* c_SW;             /* incoming short wave radiation (W/m2) */
+  double* c_LW;             /* incoming long wave radiation (W/m2) */
+  double* c_SW_dir;         /* direct short wave radiation (W/m2) */
+  double* c_LW_net;         /* net long wave radiation (W/m2) */
+  double* c_TSurfObs;       /* observed surface temperature (C) */
+  int* c_PrecPhase;         /* precipitation phase code 0..6, -9999 = interpret */
+  double* c_local_horizons; /* 360 local horizon angles (deg) */
+  double* c_Depth;          /* per-step output depth (m), < 0 = mean of layers 1,2 */
+  int* c_year;
+  int* c_month;
+  int* c_day;
+  int* c_hour;
+  int* c_minute;
+  int* c_second;
+} InputPointers;
+
+/* src/OutputPointers.f90.inc:4-17.  56 bytes.  Element i-1 receives step i; -9999.0 marks a
+ * step that was not computed (src/Initialization.f90:397-412). */
+typedef struct OutputPointers
+{
+  int outputLen;
+  double* c_TsurfOut;
+  double* c_SnowOut;
+  double* c_WaterOut;
+  double* c_IceOut;
+  double* c_DepositOut;
+  double* c_Ice2Out;
+} OutputPointers;
+
+/* src/InputSettings.f90.inc:4-18.  56 bytes.  The Fortran type has force_tsurf at offset 12;
+ * the reference's C++ struct has no such member, so a C++ caller leaves those four bytes as
+ * padding.  This library reads offset 12 exactly as the Fortran does (true iff == 1). */
+typedef struct InputSettings
+{
+  int SimLen;
+  int use_coupling;
+  int use_relaxation;
+  int force_tsurf;
+  double DTSecs;
+  double tsurfOutputDepth;
+  int NLayers;
+  int coupling_minutes;
+  double couplingEffectReduction;
+  int outputStep;
+} InputSettings;
+
+/* src/InputParameters.f90.inc:4-91.  69 doubles, 552 bytes. */
+typedef struct InputParameters
+{
+  double NightOn, NightOff, CalmLimDay, CalmLimNgt, TrfFricNgt, TrFfricDay;
+  double Grav, SB_Const, VK_Const, LVap, LFus, WatDens, SnowDens, IceDens, DepDens, WatMHeat,
+      PorEvaF;
+  double ZRefW, ZRefT, ZeroDisp, ZMom, ZHeat, Emiss, Albedo, Albedo_surroundings, MaxPormms,
+      TClimG, DampDpth, Omega, AZ, DampWearF, AlbDry, AlbSnow, vsh1, vsh2, Poro1, Poro2, RhoB1,
+      RhoB2, Silt1, Silt2;
+  double freezing_limit_normal, snow_melting_limit_normal, ice_melting_limit_normal,
+      frost_melting_limit_normal, frost_formation_limit_normal, T4Melt_normal;
+  double TLimColdH, TLimColdL, WetSnowFormR, WetSnowMeltR;
+  double PLimSnow, PLimRain, MaxSnowmms, MaxDepmms, MaxIcemms, MaxExtmms;
+  double MissValI, MissValR;
+  double Snow2IceFac;
+  double MinPrecmm, MinWatmms, MinSnowmms, MaxWatmms, WDampLim, WWetLim, WWearLim, MinDepmms,
+      MinIcemms;
+} InputParameters;
+
+/* src/LocalParameters.f90.inc:4-15.  72 bytes.  couplingIndexI and InitLenI are consumed as
+ * 1-based step indices (src/InputOutput.f90:29, src/Initialization.f90:452). */
+typedef struct LocalParameters
+{
+  double tair_relax;
+  double VZ_relax;
+  double RH_relax;
+  int couplingIndexI;
+  double couplingTsurf;
+  double lat;
+  double lon;
+  double sky_view;
+  int InitLenI;
+} LocalParameters;
+
+/* The reference entry point, unchanged (examples/example1/src/Simulation.f90:4-6).  Runs ONE
+ * point; kept for unchanged main programs.  It round-trips host<->device per call and is
+ * therefore a correctness drop-in, not the fast path: use roadsurf_run_batch. */
+void runsimulation(OutputPointers* outPointers, const InputPointers* inPointers,
+                   const InputSettings* inSettings, const InputParameters* inputParam,
+                   const LocalParameters* localParam);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Part 2: batched and device-resident entry points                                            */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Per-point status word (bit set).  The reference only prints to stdout for these events. */
+enum
+{
+  RS_ST_FAILED = 1,           /* simulation_failed (src/InputOutput.f90:66,72,81) */
+  RS_ST_BAD_INPUT = 2,        /*   ... because of an input range check */
+  RS_ST_ABNORMAL_TSURF = 4,   /*   ... because |TsurfAve| > 100 */
+  RS_ST_COUPLING_USED = 8,    /* coupling was active for this point */
+  RS_ST_COUPLING_FAILED = 16, /* Coupling_failed at the end (src/Coupling.f90:324-360,400,451) */
+  RS_ST_BL_NOT_CONVERGED = 32,/* BLCond iteration hit MaxIter (src/BoundaryLayer.f90:98-101) */
+  RS_ST_SOLAR_GEOMETRY = 64,  /* the reference would `stop` (src/SunPosition.f90:144-146,176-178) */
+  RS_ST_BAD_WINDOW = 128,     /* device SoA entry: coupling windows differ inside one warp */
+  RS_ST_NOT_RUN = 256         /* point was skipped (bad settings) */
+};
+
+/* Return codes. */
+enum
+{
+  RS_OK = 0,
+  RS_ERR_NO_DEVICE = -1,
+  RS_ERR_BAD_ARGUMENT = -2,
+  RS_ERR_CUDA = -3,
+  RS_ERR_UNSUPPORTED = -4
+};
+
+/* Text of the last error on the calling thread ("" if none). */
+const char* roadsurf_last_error(void);
+
+/* Number of visible CUDA devices (0 if none); never fails. */
+int roadsurf_device_count(void);
+
+/* Batched form of runsimulation over `npoints` independent points with shared settings and
+ * parameters (what run_locations_async does point by point,
+ * examples/example1/src/roadrunner.cpp:423-501).  Host array-of-pointers in, same arrays out.
+ * Points are split into contiguous shards over `ngpus` devices (<= 0: all visible devices).
+ * `status` (may be NULL) receives one status word per point.  Returns RS_OK or an error code;
+ * never falls back to the CPU. */
+int roadsurf_run_batch(int npoints, OutputPointers* const* out, const InputPointers* const* in,
+                       const InputSettings* settings, const InputParameters* params,
+                       const LocalParameters* const* local, int ngpus, int* status);
+
+/* Statistics of the most recent roadsurf_run_batch on this thread. */
+typedef struct RsBatchStats
+{
+  double pack_ms;        /* host AoS -> pinned SoA */
+  double h2d_ms;         /* host -> device copies (event timed) */
+  double kernel_ms;      /* step kernel(s) */
+  double d2h_ms;         /* device -> host copies */
+  double unpack_ms;      /* pinned SoA -> caller's arrays */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int64_t executed_steps; /* point-steps actually executed, including coupling re-runs */
+  int kernel_launches;
+  int groups;            /* (time axis, coupling window) groups the batch was split into */
+} RsBatchStats;
+void roadsurf_last_batch_stats(RsBatchStats* stats);
+
+/* ---- device-resident structure-of-arrays entry ------------------------------------------- */
+
+/* Planes of the forcing tensor, in order.  All fp64; PrecPhase is stored as an exact double. */
+enum
+{
+  RS_F_TAIR = 0,
+  RS_F_TDEW,
+  RS_F_VZ,
+  RS_F_RHZ,
+  RS_F_PREC,
+  RS_F_SW,
+  RS_F_LW,
+  RS_F_SWDIR,
+  RS_F_LWNET,
+  RS_F_TSURFOBS,
+  RS_F_PHASE,
+  RS_F_NVAR = 11,
+  RS_F_DEPTH = 11,      /* optional 12th plane */
+  RS_F_NVAR_DEPTH = 12
+};
+
+/* Planes of the per-point static tensor. */
+enum
+{
+  RS_L_TAIR_RELAX = 0,
+  RS_L_VZ_RELAX,
+  RS_L_RH_RELAX,
+  RS_L_COUPLING_TSURF,
+  RS_L_LAT,
+  RS_L_LON,
+  RS_L_SKY_VIEW,
+  RS_L_COUPLING_INDEX,  /* exact integer stored as double */
+  RS_L_INIT_LEN,        /* exact integer stored as double */
+  RS_L_NLOCAL = 9
+};
+
+/* Output planes. */
+enum
+{
+  RS_O_TSURF = 0,
+  RS_O_SNOW,
+  RS_O_WATER,
+  RS_O_ICE,
+  RS_O_DEPOSIT,
+  RS_O_ICE2,
+  RS_O_NVAR = 6
+};
+
+/* Everything a launch needs, as DEVICE pointers (on the current device).  `ld` is the padded
+ * point count: a multiple of 32, >= npoints; all planes have `ld` as their fastest dimension so
+ * that a warp touches one contiguous 256-byte segment per plane. */
+typedef struct RsDeviceBatch
+{
+  int npoints;
+  int ld;
+  int sim_len;          /* SimLen: number of model steps */
+  int forcing_mode;     /* 0: one forcing record per model step.  1: coarse records, linear
+                           interpolation in time on the device (JsonSource.cpp:49-176). */
+  int n_records;        /* forcing_mode 0: == sim_len.  1: number of coarse records */
+  int nvar;             /* RS_F_NVAR or RS_F_NVAR_DEPTH */
+  const double* forcing;      /* [n_records][nvar][ld] */
+  const int* record_step;     /* forcing_mode 1: 0-based model step index of every record
+                                 (strictly increasing, record_step[0] <= 0); else NULL */
+  const int* time_fields;     /* [6][sim_len]: year, month, day, hour, minute, second */
+  const double* local;        /* [RS_L_NLOCAL][ld] */
+  const double* horizons;     /* [360][ld] local horizon angles, or NULL (all zero) */
+  double* out;                /* [RS_O_NVAR][n_out][ld] */
+  int out_stride;             /* write step i (1-based) when (i-1) % out_stride == 0 */
+  int n_out;                  /* ceil(sim_len / out_stride) */
+  int* status;                /* [ld] status words (written) */
+  double* state;              /* optional [RS_STATE_NPLANES(NLayers)][ld] end-of-run state dump,
+                                 or NULL */
+  unsigned long long* counters; /* optional [RS_CNT_N] device counters (accumulated), or NULL */
+} RsDeviceBatch;
+
+enum
+{
+  RS_CNT_EXECUTED_STEPS = 0, /* point-steps executed incl. coupling re-runs */
+  RS_CNT_BL_ITERATIONS,      /* boundary layer iterations summed over point-steps */
+  RS_CNT_COUPLING_PASSES,    /* warp-level passes over a coupling window */
+  RS_CNT_FAILED_POINTS,
+  RS_CNT_N = 8
+};
+
+/* Number of fp64 planes of the end-of-run state dump for a given NLayers. */
+#define RS_STATE_NPLANES(nlayers) ((nlayers) + 2 + 12)
+
+/* Upload settings + parameters for subsequent roadsurf_run_device calls on the current device
+ * (derives layer geometry, conductivities and log terms: src/Initialization.f90:181-358,
+ * src/BalanceModel.f90:158-186,254-279).  Returns RS_OK or an error. */
+int roadsurf_set_model(const InputSettings* settings, const InputParameters* params);
+
+/* Launch the step kernel over a device-resident batch on `stream` (a cudaStream_t passed as
+ * void*; NULL = default stream).  Asynchronous.  Returns RS_OK or an error code. */
+int roadsurf_run_device(const RsDeviceBatch* batch, void* stream);
+
+/* Pack kernels for callers that hold point-major data on the device:
+ * src[point][n] (row stride `src_ld` elements) -> dst plane [n][ld].  Asynchronous. */
+int roadsurf_transpose_to_soa(const double* src, int64_t src_ld, int npoints, int n, double* dst,
+                              int ld, void* stream);
+int roadsurf_transpose_from_soa(const double* src, int ld, int npoints, int n, double* dst,
+                                int64_t dst_ld, void* stream);
+
+/* Fill n doubles with `value` (used for the -9999.0 output pre-fill).  Asynchronous. */
+int roadsurf_fill(double* dst, int64_t n, double value, void* stream);
+
+/* Measure the fp64 FMA throughput of the current device (TFLOP/s, FMA = 2 flop) with a
+ * register-resident DFMA kernel; used as the fp64 roofline denominator by bench.py. */
+double roadsurf_measure_fp64_tflops(int iterations);
+
+/* Name of the most recently launched step kernel variant and its launch geometry. */
+typedef struct RsLaunchInfo
+{
+  int grid;
+  int block;
+  int smem_bytes;
+  int regs_per_thread;
+  int nlayers;
+  int forcing_mode;
+  int launches_total;   /* kernels launched by this library in this process so far */
+} RsLaunchInfo;
+void roadsurf_last_launch(RsLaunchInfo* info);
+
+/* Library version string. */
+const char* roadsurf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ROADSURF_B200_H */

@@ -1,0 +1,108 @@
+"""ctypes loader for the CPU oracle (oracle/roadsurf_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+legs; never by the roadsurf_b200 package.  PARITY UNPINNED (see roadsurf_oracle.hpp).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from roadsurf_b200 import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "_build")
+
+
+def build(force=False):
+    """Compile both oracle flavours with oracle/Makefile (gcc only; a few seconds)."""
+    if force:
+        subprocess.run(["make", "-C", HERE, "clean"], check=True, capture_output=True)
+    r = subprocess.run(["make", "-C", HERE], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+
+
+_P = C.POINTER
+
+
+def _declare(lib):
+    OP, IP, IS, IPa, LP = (abi.OutputPointers, abi.InputPointers, abi.InputSettings,
+                           abi.InputParameters, abi.LocalParameters)
+    lib.oracle_runsimulation.argtypes = [_P(OP), _P(IP), _P(IS), _P(IPa), _P(LP)]
+    lib.oracle_runsimulation.restype = None
+    lib.oracle_runsimulation_ex.argtypes = [_P(OP), _P(IP), _P(IS), _P(IPa), _P(LP),
+                                            _P(C.c_longlong), _P(C.c_longlong), C.c_int]
+    lib.oracle_runsimulation_ex.restype = C.c_int
+    lib.oracle_run_batch.argtypes = [C.c_int, _P(_P(OP)), _P(_P(IP)), _P(IS), _P(IPa), _P(_P(LP)),
+                                     C.c_int, _P(C.c_int), _P(C.c_longlong)]
+    lib.oracle_run_batch.restype = None
+    lib.oracle_count_ops.argtypes = [_P(OP), _P(IP), _P(IS), _P(IPa), _P(LP), _P(C.c_ulonglong)]
+    lib.oracle_count_ops.restype = C.c_longlong
+    lib.oracle_layer_depths.argtypes = [C.c_int, abi.c_double_p]
+    lib.oracle_ground_constants.argtypes = [_P(IS), _P(IPa)] + [abi.c_double_p] * 4
+    lib.oracle_julday.argtypes = [C.c_int] * 3
+    lib.oracle_julday.restype = C.c_int
+    lib.oracle_jde.argtypes = [C.c_int] * 6
+    lib.oracle_jde.restype = C.c_double
+    lib.oracle_sun_position.argtypes = [C.c_int] * 6 + [C.c_double, C.c_double, abi.c_double_p,
+                                                         abi.c_double_p]
+    lib.oracle_sun_position.restype = C.c_int
+    lib.oracle_calc_tdew.argtypes = [C.c_double, C.c_double]
+    lib.oracle_calc_tdew.restype = C.c_double
+    lib.oracle_calc_rh.argtypes = [C.c_double, C.c_double]
+    lib.oracle_calc_rh.restype = C.c_double
+    lib.oracle_prec_type.argtypes = [_P(IS), _P(IPa), C.c_int, C.c_double, C.c_double, C.c_double,
+                                     abi.c_double_p, abi.c_double_p]
+    lib.oracle_prec_type.restype = C.c_int
+    lib.oracle_boundary_layer.argtypes = [_P(IS), _P(IPa)] + [C.c_double] * 5 + [abi.c_double_p]
+    lib.oracle_boundary_layer.restype = C.c_int
+    lib.oracle_road_cond.argtypes = [_P(IS), _P(IPa), abi.c_double_p]
+    lib.oracle_coupling_control.argtypes = [abi.c_double_p, abi.c_int_p]
+    lib.oracle_build_flavour.restype = C.c_char_p
+    return lib
+
+
+_libs = {}
+
+
+def load(fast=False):
+    """Load (building if needed) the parity oracle, or with fast=True the flavour compiled with
+    the reference's -Ofast flag set (CPU timing baseline)."""
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    if name not in _libs:
+        path = os.path.join(BUILD, name)
+        if not os.path.exists(path):
+            build()
+        _libs[name] = _declare(C.CDLL(path))
+    return _libs[name]
+
+
+def run_batch(arrays, settings, params, nthreads=1, fast=False):
+    """Run every point of a PointArrays through the oracle (mutates arrays' inputs exactly as the
+    reference does, fills arrays.out).  Returns (status[npoints], executed_steps)."""
+    lib = load(fast)
+    ins = arrays.input_pointers()
+    outs = arrays.output_pointers()
+    in_ptrs = abi.pointer_arrays(ins, abi.InputPointers)
+    out_ptrs = abi.pointer_arrays(outs, abi.OutputPointers)
+    loc_ptrs = abi.pointer_arrays(arrays.local, abi.LocalParameters)
+    status = np.zeros(arrays.npoints, dtype=np.int32)
+    steps = C.c_longlong(0)
+    lib.oracle_run_batch(arrays.npoints, out_ptrs, in_ptrs, C.byref(settings), C.byref(params),
+                         loc_ptrs, int(nthreads), status.ctypes.data_as(abi.c_int_p),
+                         C.byref(steps))
+    return status, steps.value
+
+
+def count_ops(arrays, settings, params, point=0):
+    """Exact arithmetic-operation counts of one point's run: dict + executed step count."""
+    lib = load(False)
+    ins = arrays.input_pointers()
+    outs = arrays.output_pointers()
+    counts = (C.c_ulonglong * 9)()
+    steps = lib.oracle_count_ops(C.byref(outs[point]), C.byref(ins[point]), C.byref(settings),
+                                 C.byref(params), C.byref(arrays.local[point]), counts)
+    names = ("add", "mul", "div", "sqrt", "exp", "log", "trig", "pow", "cmp")
+    return dict(zip(names, [int(c) for c in counts])), int(steps)
