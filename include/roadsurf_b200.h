@@ -224,7 +224,8 @@ enum
   RS_L_SKY_VIEW,
   RS_L_COUPLING_INDEX,  /* exact integer stored as double */
   RS_L_INIT_LEN,        /* exact integer stored as double */
-  RS_L_NLOCAL = 9
+  RS_L_ACTIVE,          /* 1.0 = a real point, 0.0 = padding slot (never run) */
+  RS_L_NLOCAL = 10
 };
 
 /* Output planes. */
@@ -263,6 +264,8 @@ typedef struct RsDeviceBatch
   int* status;                /* [ld] status words (written) */
   double* state;              /* optional [RS_STATE_NPLANES(NLayers)][ld] end-of-run state dump,
                                  or NULL */
+  double* scratch;            /* [RS_SCRATCH_NPLANES(NLayers)][ld] work space; required when the
+                                 model has use_coupling == 1, else may be NULL */
   unsigned long long* counters; /* optional [RS_CNT_N] device counters (accumulated), or NULL */
 } RsDeviceBatch;
 
@@ -277,6 +280,8 @@ enum
 
 /* Number of fp64 planes of the end-of-run state dump for a given NLayers. */
 #define RS_STATE_NPLANES(nlayers) ((nlayers) + 2 + 12)
+/* Number of fp64 planes of the coupling work space (window snapshot + bracket scalars). */
+#define RS_SCRATCH_NPLANES(nlayers) (2 * (nlayers) + 16)
 
 /* Upload settings + parameters for subsequent roadsurf_run_device calls on the current device
  * (derives layer geometry, conductivities and log terms: src/Initialization.f90:181-358,
@@ -286,6 +291,36 @@ int roadsurf_set_model(const InputSettings* settings, const InputParameters* par
 /* Launch the step kernel over a device-resident batch on `stream` (a cudaStream_t passed as
  * void*; NULL = default stream).  Asynchronous.  Returns RS_OK or an error code. */
 int roadsurf_run_device(const RsDeviceBatch* batch, void* stream);
+
+/* ---- host structure-of-arrays entry (coarse forcing records + strided output) ---------------- */
+
+/* The same batch as RsDeviceBatch but with HOST pointers and no padding (leading dimension =
+ * npoints).  This is the host-buffer form of the coarse-forcing / strided-output interface: the
+ * library copies the records to the device(s), interpolates them in time inside the kernel
+ * (examples/example1/src/JsonSource.cpp:49-176), and copies the strided outputs
+ * (examples/example1/src/roadrunner.cpp:285-327: every outputStep) back.  Pinned host memory is
+ * recommended (the copies are asynchronous and chunk-pipelined), pageable memory works. */
+typedef struct RsHostBatch
+{
+  int npoints;
+  int sim_len;
+  int forcing_mode;           /* 0: one record per model step, 1: coarse records */
+  int n_records;
+  int nvar;                   /* RS_F_NVAR or RS_F_NVAR_DEPTH */
+  int out_stride;
+  const double* forcing;      /* [n_records][nvar][npoints] */
+  const int* record_step;     /* [n_records] (forcing_mode 1) */
+  const int* time_fields;     /* [6][sim_len] */
+  const double* local;        /* [RS_L_NLOCAL][npoints] */
+  const double* horizons;     /* [360][npoints] or NULL */
+  double* out;                /* [RS_O_NVAR][n_out][npoints], n_out = ceil(sim_len / out_stride) */
+  int* status;                /* [npoints] or NULL */
+} RsHostBatch;
+
+/* Runs a host SoA batch on `ngpus` devices (<= 0: all visible; 1: the current device), points
+ * split into contiguous shards.  Synchronous.  Statistics via roadsurf_last_batch_stats. */
+int roadsurf_run_host_soa(const RsHostBatch* batch, const InputSettings* settings,
+                          const InputParameters* params, int ngpus);
 
 /* Pack kernels for callers that hold point-major data on the device:
  * src[point][n] (row stride `src_ld` elements) -> dst plane [n][ld].  Asynchronous. */

@@ -35,6 +35,8 @@ def _declare(lib):
     lib.oracle_runsimulation_ex.argtypes = [_P(OP), _P(IP), _P(IS), _P(IPa), _P(LP),
                                             _P(C.c_longlong), _P(C.c_longlong), C.c_int]
     lib.oracle_runsimulation_ex.restype = C.c_int
+    lib.oracle_trace_point.argtypes = [_P(OP), _P(IP), _P(IS), _P(IPa), _P(LP), abi.c_double_p]
+    lib.oracle_trace_point.restype = C.c_int
     lib.oracle_run_batch.argtypes = [C.c_int, _P(_P(OP)), _P(_P(IP)), _P(IS), _P(IPa), _P(_P(LP)),
                                      C.c_int, _P(C.c_int), _P(C.c_longlong)]
     lib.oracle_run_batch.restype = None
@@ -106,3 +108,18 @@ def count_ops(arrays, settings, params, point=0):
                                  C.byref(params), C.byref(arrays.local[point]), counts)
     names = ("add", "mul", "div", "sqrt", "exp", "log", "trig", "pow", "cmp")
     return dict(zip(names, [int(c) for c in counts])), int(steps)
+
+
+TRACE_NAMES = ("Ts_in", "Tair", "Prec", "Q2Melt_in", "rain", "snow", "Snow_preRC", "Wat_preRC", "Ice_preRC",
+               "Q2Melt_preRC", "T1", "T2", "HStor", "BLCond", "LE", "Evap")
+
+
+def trace_point(arrays, settings, params, point=0):
+    """Per-step internals of one point's oracle run: numpy [sim_len, 16] (columns TRACE_NAMES)."""
+    lib = load(False)
+    ins = arrays.input_pointers()
+    outs = arrays.output_pointers()
+    tr = np.zeros((arrays.sim_len, 16))
+    lib.oracle_trace_point(C.byref(outs[point]), C.byref(ins[point]), C.byref(settings), C.byref(params),
+                           C.byref(arrays.local[point]), tr.ctypes.data_as(abi.c_double_p))
+    return tr

@@ -96,6 +96,16 @@ int oracle_runsimulation_ex(OutputPointers* out, const InputPointers* in, const 
   return status_word(m);
 }
 
+// One point with a per-step trace of internals: trace[SimLen][16] (see roadModelOneStep).
+int oracle_trace_point(OutputPointers* out, const InputPointers* in, const InputSettings* settings,
+                       const InputParameters* params, const LocalParameters* local, double* trace)
+{
+  Model<double> m;
+  m.diag.trace = trace;
+  m.runsimulation(*out, *in, *settings, *params, *local);
+  return status_word(m);
+}
+
 // Work-queue over points on `nthreads` host threads: the equivalent of example1's `-j N`
 // (examples/example1/src/WorkQueue.h:15-130, roadrunner.cpp:423-501).  Used for the CPU baseline.
 void oracle_run_batch(int npoints, OutputPointers* const* out, const InputPointers* const* in,

@@ -183,7 +183,10 @@ struct Diagnostics
   bool bad_input = false;
   bool abnormal_tsurf = false;
   bool verbose = false;
+  // optional per-step trace [SimLen][TRACE_N] (last visit of a step wins); see roadModelOneStep
+  double* trace = nullptr;
 };
+constexpr int TRACE_N = 16;
 
 template <class R>
 struct Model
@@ -1927,10 +1930,33 @@ struct Model
   void roadModelOneStep(int input_idxI, const InputParameters& ip, const LocalParameters& lp)
   {
     WearingFactors<R> wearF;
+    double* tr = diag.trace ? diag.trace + static_cast<size_t>(input_idxI - 1) * TRACE_N : nullptr;
+    if (tr)
+    {
+      tr[0] = r_val(surf.TsurfAve);
+      tr[1] = r_val(atm.Tair);
+      tr[2] = r_val(atm.PrecInTStep);
+      tr[3] = r_val(surf.Q2Melt);
+    }
     PrecipitationToStorage(modelInput.PrecPhase[input_idxI - 1]);
     if (sky_view_active(lp)) ModRadiationBySurroundings(ip, lp, input_idxI);
     BalanceModelOneStep(R(modelInput.SW[input_idxI - 1]), R(modelInput.LW[input_idxI - 1]),
                         input_idxI);
+    if (tr)
+    {
+      tr[4] = r_val(atm.RainmmTS);
+      tr[5] = r_val(atm.SnowmmTS);
+      tr[6] = r_val(surf.SrfSnowmms);
+      tr[7] = r_val(surf.SrfWatmms);
+      tr[8] = r_val(surf.SrfIcemms);
+      tr[9] = r_val(surf.Q2Melt);
+      tr[10] = r_val(ground.Tmp[1]);
+      tr[11] = r_val(ground.Tmp[2]);
+      tr[12] = r_val(ground.HStor);
+      tr[13] = r_val(atm.BLCond);
+      tr[14] = r_val(atm.LE_Flux);
+      tr[15] = r_val(surf.EvapmmTS);
+    }
     WearFactors(wearF);
     RoadCond(phy.MaxPormms, wearF);
     CalcAlbedo();

@@ -79,7 +79,7 @@ assert LocalParameters.couplingTsurf.offset == 32 and LocalParameters.InitLenI.o
 
 def default_settings(sim_len, use_coupling=0, use_relaxation=0, dt=30.0, nlayers=15,
                      coupling_minutes=180, force_tsurf=0, tsurf_output_depth=-9999.9,
-                     coupling_effect_reduction=4.0 * 3600, output_step=60):
+                     coupling_effect_reduction=4.0 * 3600, output_step=60):  # noqa: D401
     """examples/example1/src/InputSettings.h:13-23."""
     return InputSettings(SimLen=int(sim_len), use_coupling=int(use_coupling),
                          use_relaxation=int(use_relaxation), force_tsurf=int(force_tsurf),

@@ -1,0 +1,865 @@
+// rs_host.cu -- the C ABI of libroadsurf_b200.so (include/roadsurf_b200.h): model upload, the
+// device-resident launch, the batched host entry (pack -> H2D -> kernel -> D2H -> unpack, sharded
+// over GPUs) and the reference's single-point `runsimulation`.
+//
+// There is no CPU implementation of the model in this library: every entry point either runs the
+// CUDA kernel or returns an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "rs_kernel.cuh"
+
+namespace
+{
+thread_local std::string g_err;
+thread_local RsBatchStats g_stats;
+thread_local RsLaunchInfo g_launch;
+std::mutex g_model_mu;
+std::map<int, RsModel> g_models;  // device -> model currently in its constant memory
+int g_launches_total = 0;
+
+int fail(int code, const std::string& msg)
+{
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                    \
+  do                                                                                                \
+  {                                                                                                 \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      return fail(RS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+  } while (0)
+
+double now_ms()
+{
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+int set_model_on_current_device(const InputSettings* settings, const InputParameters* params, RsModel* out)
+{
+  RsModel m;
+  char err[256];
+  const int rc = rs_build_model(settings, params, &m, err, sizeof err);
+  if (rc != RS_OK) return fail(rc, err);
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  CU(static_cast<cudaError_t>(rs_upload_model(&m)));
+  {
+    std::lock_guard<std::mutex> lk(g_model_mu);
+    g_models[dev] = m;
+  }
+  if (out) *out = m;
+  return RS_OK;
+}
+
+struct DeviceMem
+{
+  void* p = nullptr;
+  ~DeviceMem()
+  {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+  template <class T>
+  T* as() const
+  {
+    return static_cast<T*>(p);
+  }
+};
+
+struct PinnedMem
+{
+  void* p = nullptr;
+  ~PinnedMem()
+  {
+    if (p) cudaFreeHost(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMallocHost(&p, bytes ? bytes : 8); }
+  template <class T>
+  T* as() const
+  {
+    return static_cast<T*>(p);
+  }
+};
+
+// What the kernel will decide about a point's coupling window (src/InputOutput.f90:34-36,
+// src/Coupling.f90:510-519): used only to order slots so that every warp has one window.
+long long window_key(const RsModel& m, const LocalParameters& lp)
+{
+  if (!m.use_coupling || lp.couplingTsurf < -100 || lp.couplingIndexI < 1) return -1;
+  return lp.couplingIndexI;
+}
+
+struct Shard
+{
+  int first = 0, count = 0, device = 0;
+  int rc = RS_OK;
+  std::string err;
+  RsBatchStats stats{};
+  RsLaunchInfo launch{};
+};
+
+// Run points [first, first+count) of the batch on `device`.
+int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const* in,
+              const InputSettings* settings, const InputParameters* params,
+              const LocalParameters* const* local, int* status)
+{
+  CU(cudaSetDevice(sh.device));
+  RsModel model;
+  {
+    const int rc = set_model_on_current_device(settings, params, &model);
+    if (rc != RS_OK) return rc;
+  }
+  const int sim_len = settings->SimLen;
+  const int nl = model.nlayers;
+  cudaStream_t stream;
+  CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  struct StreamGuard
+  {
+    cudaStream_t s;
+    ~StreamGuard() { cudaStreamDestroy(s); }
+  } sguard{stream};
+
+  // ---- group points by time axis; inside a group order slots by coupling window ----------------
+  struct Group
+  {
+    const InputPointers* rep;
+    std::vector<int> points;
+  };
+  std::vector<Group> groups;
+  for (int q = 0; q < sh.count; ++q)
+  {
+    const int p = sh.first + q;
+    const InputPointers* ip = in[p];
+    if (ip->inputLen < sim_len || out[p]->outputLen < sim_len)
+      return fail(RS_ERR_BAD_ARGUMENT, "inputLen/outputLen shorter than SimLen");
+    bool placed = false;
+    for (auto& g : groups)
+    {
+      const InputPointers* r = g.rep;
+      const bool same_ptr = r->c_year == ip->c_year && r->c_month == ip->c_month && r->c_day == ip->c_day &&
+                            r->c_hour == ip->c_hour && r->c_minute == ip->c_minute && r->c_second == ip->c_second;
+      const size_t nb = sizeof(int) * sim_len;
+      if (same_ptr || (!std::memcmp(r->c_year, ip->c_year, nb) && !std::memcmp(r->c_month, ip->c_month, nb) &&
+                       !std::memcmp(r->c_day, ip->c_day, nb) && !std::memcmp(r->c_hour, ip->c_hour, nb) &&
+                       !std::memcmp(r->c_minute, ip->c_minute, nb) && !std::memcmp(r->c_second, ip->c_second, nb)))
+      {
+        g.points.push_back(p);
+        placed = true;
+        break;
+      }
+    }
+    if (!placed) groups.push_back(Group{ip, {p}});
+  }
+
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+
+  for (auto& g : groups)
+  {
+    // slots: windows sorted, each window padded to a warp boundary; uncoupled points fill the gaps
+    std::map<long long, std::vector<int>> by_window;
+    for (int p : g.points) by_window[window_key(model, *local[p])].push_back(p);
+    std::vector<int> slots;  // point index or -1 (padding)
+    std::vector<int> loose;
+    if (by_window.count(-1)) loose = by_window[-1];
+    size_t loose_pos = 0;
+    for (auto& kv : by_window)
+    {
+      if (kv.first == -1) continue;
+      for (int p : kv.second) slots.push_back(p);
+      while (slots.size() % 32 != 0)
+      {
+        if (loose_pos < loose.size())
+          slots.push_back(loose[loose_pos++]);
+        else
+          slots.push_back(-1);
+      }
+    }
+    while (loose_pos < loose.size()) slots.push_back(loose[loose_pos++]);
+    while (slots.size() % 32 != 0) slots.push_back(-1);
+    ++sh.stats.groups;
+
+    bool any_depth = false, any_sky = false;
+    for (int p : g.points)
+    {
+      const LocalParameters& lp = *local[p];
+      if (lp.sky_view < 1.0 && lp.sky_view > -0.01f) any_sky = true;
+      if (!any_depth)  // depth(1) and depth(SimLen) are read even when tsurfOutputDepth is set
+      {
+        const double* d = in[p]->c_Depth;
+        for (int t = 0; t < sim_len; ++t)
+          if (d[t] >= 0.0)
+          {
+            any_depth = true;
+            break;
+          }
+      }
+    }
+    const int nvar = any_depth ? RS_F_NVAR_DEPTH : RS_F_NVAR;
+
+    // ---- device batches that fit the memory budget -------------------------------------------
+    const size_t per_slot = sizeof(double) * (static_cast<size_t>(sim_len) * (nvar + RS_O_NVAR) + RS_L_NLOCAL +
+                                              (any_sky ? 360 : 0) + RS_SCRATCH_NPLANES(nl)) + sizeof(int);
+    size_t budget = static_cast<size_t>(free_b * 0.80);
+    size_t max_slots = budget / per_slot / 32 * 32;
+    if (max_slots < 32) return fail(RS_ERR_CUDA, "not enough device memory for one warp of points");
+    // staging chunk: <= 192 MiB of pinned memory per direction
+    const size_t stage_budget = 192ull << 20;
+    int chunk = static_cast<int>(std::max<size_t>(32, stage_budget / (sizeof(double) * sim_len * nvar) / 32 * 32));
+
+    DeviceMem d_tf;
+    CU(d_tf.alloc(sizeof(int) * 6 * sim_len));
+    {
+      const int* src[6] = {g.rep->c_year, g.rep->c_month, g.rep->c_day, g.rep->c_hour, g.rep->c_minute,
+                           g.rep->c_second};
+      for (int k = 0; k < 6; ++k)
+        CU(cudaMemcpyAsync(d_tf.as<int>() + static_cast<size_t>(k) * sim_len, src[k], sizeof(int) * sim_len,
+                           cudaMemcpyHostToDevice, stream));
+      sh.stats.h2d_bytes += sizeof(int) * 6 * sim_len;
+    }
+
+    for (size_t s0 = 0; s0 < slots.size(); s0 += max_slots)
+    {
+      const int ld = static_cast<int>(std::min(max_slots, slots.size() - s0));
+      chunk = std::min(chunk, ld);
+      DeviceMem d_forcing, d_out, d_local, d_hor, d_status, d_scratch, d_stage, d_counters;
+      CU(d_forcing.alloc(sizeof(double) * sim_len * nvar * ld));
+      CU(d_out.alloc(sizeof(double) * RS_O_NVAR * sim_len * ld));
+      CU(d_local.alloc(sizeof(double) * RS_L_NLOCAL * ld));
+      if (any_sky) CU(d_hor.alloc(sizeof(double) * 360 * ld));
+      CU(d_status.alloc(sizeof(int) * ld));
+      if (model.use_coupling) CU(d_scratch.alloc(sizeof(double) * RS_SCRATCH_NPLANES(nl) * ld));
+      CU(d_stage.alloc(sizeof(double) * static_cast<size_t>(chunk) * sim_len * std::max(nvar, (int)RS_O_NVAR)));
+      CU(d_counters.alloc(sizeof(unsigned long long) * RS_CNT_N));
+      CU(cudaMemsetAsync(d_counters.p, 0, sizeof(unsigned long long) * RS_CNT_N, stream));
+      PinnedMem h_stage, h_local, h_hor, h_status;
+      CU(h_stage.alloc(sizeof(double) * static_cast<size_t>(chunk) * sim_len * std::max(nvar, (int)RS_O_NVAR)));
+      CU(h_local.alloc(sizeof(double) * RS_L_NLOCAL * ld));
+      if (any_sky) CU(h_hor.alloc(sizeof(double) * 360 * ld));
+      CU(h_status.alloc(sizeof(int) * ld));
+
+      cudaEvent_t ev0, ev1;
+      CU(cudaEventCreate(&ev0));
+      CU(cudaEventCreate(&ev1));
+      struct EvGuard
+      {
+        cudaEvent_t a, b;
+        ~EvGuard()
+        {
+          cudaEventDestroy(a);
+          cudaEventDestroy(b);
+        }
+      } eguard{ev0, ev1};
+
+      // ---- per-point statics
+      double t0 = now_ms();
+      {
+        double* L = h_local.as<double>();
+        for (int q = 0; q < ld; ++q)
+        {
+          const int p = slots[s0 + q];
+          LocalParameters lp;
+          std::memset(&lp, 0, sizeof lp);
+          if (p >= 0) lp = *local[p];
+          L[RS_L_TAIR_RELAX * (size_t)ld + q] = lp.tair_relax;
+          L[RS_L_VZ_RELAX * (size_t)ld + q] = lp.VZ_relax;
+          L[RS_L_RH_RELAX * (size_t)ld + q] = lp.RH_relax;
+          L[RS_L_COUPLING_TSURF * (size_t)ld + q] = lp.couplingTsurf;
+          L[RS_L_LAT * (size_t)ld + q] = lp.lat;
+          L[RS_L_LON * (size_t)ld + q] = lp.lon;
+          L[RS_L_SKY_VIEW * (size_t)ld + q] = (p >= 0) ? lp.sky_view : 1.0;
+          L[RS_L_COUPLING_INDEX * (size_t)ld + q] = lp.couplingIndexI;
+          L[RS_L_INIT_LEN * (size_t)ld + q] = lp.InitLenI;
+          L[RS_L_ACTIVE * (size_t)ld + q] = (p >= 0) ? 1.0 : 0.0;
+        }
+        if (any_sky)
+        {
+          double* H = h_hor.as<double>();
+          for (int q = 0; q < ld; ++q)
+          {
+            const int p = slots[s0 + q];
+            const double* src = (p >= 0) ? in[p]->c_local_horizons : nullptr;
+            for (int k = 0; k < 360; ++k) H[static_cast<size_t>(k) * ld + q] = src ? src[k] : 0.0;
+          }
+        }
+      }
+      sh.stats.pack_ms += now_ms() - t0;
+      CU(cudaMemcpyAsync(d_local.p, h_local.p, sizeof(double) * RS_L_NLOCAL * ld, cudaMemcpyHostToDevice, stream));
+      sh.stats.h2d_bytes += sizeof(double) * RS_L_NLOCAL * ld;
+      if (any_sky)
+      {
+        CU(cudaMemcpyAsync(d_hor.p, h_hor.p, sizeof(double) * 360 * ld, cudaMemcpyHostToDevice, stream));
+        sh.stats.h2d_bytes += sizeof(double) * 360 * ld;
+      }
+
+      // ---- forcing: caller's per-point arrays -> pinned [var][point][time] -> device -> SoA
+      for (int q0 = 0; q0 < ld; q0 += chunk)
+      {
+        const int npc = std::min(chunk, ld - q0);
+        t0 = now_ms();
+        double* S = h_stage.as<double>();
+        for (int q = 0; q < npc; ++q)
+        {
+          const int p = slots[s0 + q0 + q];
+          const size_t row = static_cast<size_t>(q) * sim_len;
+          const size_t plane = static_cast<size_t>(npc) * sim_len;
+          if (p < 0)
+          {
+            for (int v = 0; v < nvar; ++v) std::memset(S + v * plane + row, 0, sizeof(double) * sim_len);
+            continue;
+          }
+          const InputPointers* ip = in[p];
+          const double* src[RS_F_NVAR_DEPTH] = {ip->c_tair, ip->c_tdew, ip->c_VZ,     ip->c_Rhz,
+                                                ip->c_prec, ip->c_SW,   ip->c_LW,     ip->c_SW_dir,
+                                                ip->c_LW_net, ip->c_TSurfObs, nullptr, ip->c_Depth};
+          for (int v = 0; v < nvar; ++v)
+          {
+            double* dst = S + v * plane + row;
+            if (v == RS_F_PHASE)
+              for (int t = 0; t < sim_len; ++t) dst[t] = static_cast<double>(ip->c_PrecPhase[t]);
+            else
+              std::memcpy(dst, src[v], sizeof(double) * sim_len);
+          }
+        }
+        sh.stats.pack_ms += now_ms() - t0;
+        const size_t bytes = sizeof(double) * static_cast<size_t>(npc) * sim_len * nvar;
+        CU(cudaEventRecord(ev0, stream));
+        CU(cudaMemcpyAsync(d_stage.p, h_stage.p, bytes, cudaMemcpyHostToDevice, stream));
+        CU(cudaEventRecord(ev1, stream));
+        CU(static_cast<cudaError_t>(rs_launch_pack_forcing(d_stage.as<double>(), npc, q0, sim_len, nvar,
+                                                           d_forcing.as<double>(), ld, stream)));
+        ++sh.stats.kernel_launches;
+        CU(cudaStreamSynchronize(stream));  // the pinned staging buffer is reused by the next chunk
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        sh.stats.h2d_ms += ms;
+        sh.stats.h2d_bytes += bytes;
+      }
+
+      // ---- the step kernel
+      RsArgs a;
+      std::memset(&a, 0, sizeof a);
+      a.npoints = ld;
+      a.ld = ld;
+      a.sim_len = sim_len;
+      a.n_records = sim_len;
+      a.nvar = nvar;
+      a.out_stride = 1;
+      a.n_out = sim_len;
+      a.forcing_mode = 0;
+      a.forcing = d_forcing.as<double>();
+      a.tf = d_tf.as<int>();
+      a.local = d_local.as<double>();
+      a.horizons = any_sky ? d_hor.as<double>() : nullptr;
+      a.out = d_out.as<double>();
+      a.status = d_status.as<int>();
+      a.scratch = model.use_coupling ? d_scratch.as<double>() : nullptr;
+      a.counters = d_counters.as<unsigned long long>();
+      CU(cudaEventRecord(ev0, stream));
+      CU(static_cast<cudaError_t>(
+          rs_launch_run(&a, nl, stream, &sh.launch.grid, &sh.launch.block, &sh.launch.regs_per_thread)));
+      CU(cudaEventRecord(ev1, stream));
+      ++sh.stats.kernel_launches;
+      sh.launch.nlayers = nl;
+      sh.launch.forcing_mode = 0;
+      CU(cudaStreamSynchronize(stream));
+      {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        sh.stats.kernel_ms += ms;
+      }
+
+      // ---- outputs: SoA -> [var][point][time] -> pinned -> caller's arrays
+      for (int q0 = 0; q0 < ld; q0 += chunk)
+      {
+        const int npc = std::min(chunk, ld - q0);
+        const size_t bytes = sizeof(double) * static_cast<size_t>(npc) * sim_len * RS_O_NVAR;
+        CU(static_cast<cudaError_t>(
+            rs_launch_unpack_out(d_out.as<double>(), ld, sim_len, q0, npc, d_stage.as<double>(), stream)));
+        ++sh.stats.kernel_launches;
+        CU(cudaEventRecord(ev0, stream));
+        CU(cudaMemcpyAsync(h_stage.p, d_stage.p, bytes, cudaMemcpyDeviceToHost, stream));
+        CU(cudaEventRecord(ev1, stream));
+        CU(cudaStreamSynchronize(stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        sh.stats.d2h_ms += ms;
+        sh.stats.d2h_bytes += bytes;
+        t0 = now_ms();
+        const double* S = h_stage.as<double>();
+        const size_t plane = static_cast<size_t>(npc) * sim_len;
+        for (int q = 0; q < npc; ++q)
+        {
+          const int p = slots[s0 + q0 + q];
+          if (p < 0) continue;
+          OutputPointers* op = out[p];
+          double* dst[RS_O_NVAR] = {op->c_TsurfOut, op->c_SnowOut, op->c_WaterOut,
+                                    op->c_IceOut,   op->c_DepositOut, op->c_Ice2Out};
+          for (int v = 0; v < RS_O_NVAR; ++v)
+            std::memcpy(dst[v], S + v * plane + static_cast<size_t>(q) * sim_len, sizeof(double) * sim_len);
+        }
+        sh.stats.unpack_ms += now_ms() - t0;
+      }
+      CU(cudaMemcpyAsync(h_status.p, d_status.p, sizeof(int) * ld, cudaMemcpyDeviceToHost, stream));
+      unsigned long long cnt[RS_CNT_N];
+      CU(cudaMemcpyAsync(cnt, d_counters.p, sizeof cnt, cudaMemcpyDeviceToHost, stream));
+      CU(cudaStreamSynchronize(stream));
+      sh.stats.d2h_bytes += sizeof(int) * ld;
+      sh.stats.executed_steps += static_cast<int64_t>(cnt[RS_CNT_EXECUTED_STEPS]);
+      if (status)
+        for (int q = 0; q < ld; ++q)
+        {
+          const int p = slots[s0 + q];
+          if (p >= 0) status[p] = h_status.as<int>()[q];
+        }
+    }
+  }
+  return RS_OK;
+}
+// Grow-only device work space, one per (device, slot), reused across host-SoA calls so that a
+// steady-state call does no cudaMalloc.
+struct PoolEntry
+{
+  void* p = nullptr;
+  size_t cap = 0;
+};
+std::mutex g_pool_mu;
+std::map<std::pair<int, int>, PoolEntry> g_pool;
+
+cudaError_t pool_get(int device, int slot, size_t bytes, void** out)
+{
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  PoolEntry& e = g_pool[{device, slot}];
+  if (e.cap < bytes)
+  {
+    if (e.p) cudaFree(e.p);
+    e.p = nullptr;
+    e.cap = 0;
+    cudaError_t rc = cudaMalloc(&e.p, bytes);
+    if (rc != cudaSuccess) return rc;
+    e.cap = bytes;
+  }
+  *out = e.p;
+  return cudaSuccess;
+}
+
+// Points [first, first+count) of a host SoA batch on `device`, pipelined in column chunks over two
+// streams: H2D(chunk c+1) overlaps kernel(chunk c) overlaps D2H(chunk c-1).
+int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* settings,
+                       const InputParameters* params)
+{
+  CU(cudaSetDevice(sh.device));
+  RsModel model;
+  {
+    const int rc = set_model_on_current_device(settings, params, &model);
+    if (rc != RS_OK) return rc;
+  }
+  const int nl = model.nlayers;
+  const int n_out = (b->sim_len + b->out_stride - 1) / b->out_stride;
+  const size_t np_all = static_cast<size_t>(b->npoints);
+  constexpr int NSTREAM = 2;
+  // chunk size: a multiple of 32 points, about 1/8 of the shard but at least 64 Ki points
+  int chunk = ((sh.count + 7) / 8 + 31) / 32 * 32;
+  if (chunk < 65536) chunk = std::min((sh.count + 31) / 32 * 32, 65536);
+  const int nchunks = (sh.count + chunk - 1) / chunk;
+  const size_t frows = static_cast<size_t>(b->n_records) * b->nvar;
+  const size_t orows = static_cast<size_t>(RS_O_NVAR) * n_out;
+  const bool hor = b->horizons != nullptr;
+
+  cudaStream_t streams[NSTREAM];
+  cudaEvent_t ev[NSTREAM][4];
+  for (int s = 0; s < NSTREAM; ++s)
+  {
+    CU(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
+    for (int k = 0; k < 4; ++k) CU(cudaEventCreate(&ev[s][k]));
+  }
+  struct Guard
+  {
+    cudaStream_t* st;
+    cudaEvent_t (*ev)[4];
+    ~Guard()
+    {
+      for (int s = 0; s < NSTREAM; ++s)
+      {
+        for (int k = 0; k < 4; ++k) cudaEventDestroy(ev[s][k]);
+        cudaStreamDestroy(st[s]);
+      }
+    }
+  } guard{streams, ev};
+
+  // per-stream device buffers
+  double *d_forcing[NSTREAM], *d_out[NSTREAM], *d_local[NSTREAM], *d_hor[NSTREAM], *d_scratch[NSTREAM];
+  int* d_status[NSTREAM];
+  unsigned long long* d_counters = nullptr;
+  int *d_tf = nullptr, *d_rs = nullptr;
+  void* tmp = nullptr;
+  for (int s = 0; s < NSTREAM; ++s)
+  {
+    CU(pool_get(sh.device, 10 * s + 0, sizeof(double) * frows * chunk, &tmp));
+    d_forcing[s] = static_cast<double*>(tmp);
+    CU(pool_get(sh.device, 10 * s + 1, sizeof(double) * orows * chunk, &tmp));
+    d_out[s] = static_cast<double*>(tmp);
+    CU(pool_get(sh.device, 10 * s + 2, sizeof(double) * RS_L_NLOCAL * chunk, &tmp));
+    d_local[s] = static_cast<double*>(tmp);
+    d_hor[s] = nullptr;
+    if (hor)
+    {
+      CU(pool_get(sh.device, 10 * s + 3, sizeof(double) * 360 * chunk, &tmp));
+      d_hor[s] = static_cast<double*>(tmp);
+    }
+    d_scratch[s] = nullptr;
+    if (model.use_coupling)
+    {
+      CU(pool_get(sh.device, 10 * s + 4, sizeof(double) * RS_SCRATCH_NPLANES(nl) * chunk, &tmp));
+      d_scratch[s] = static_cast<double*>(tmp);
+    }
+    CU(pool_get(sh.device, 10 * s + 5, sizeof(int) * chunk, &tmp));
+    d_status[s] = static_cast<int*>(tmp);
+  }
+  CU(pool_get(sh.device, 100, sizeof(int) * 6 * b->sim_len, &tmp));
+  d_tf = static_cast<int*>(tmp);
+  CU(pool_get(sh.device, 101, sizeof(int) * std::max(1, b->n_records), &tmp));
+  d_rs = static_cast<int*>(tmp);
+  CU(pool_get(sh.device, 102, sizeof(unsigned long long) * RS_CNT_N, &tmp));
+  d_counters = static_cast<unsigned long long*>(tmp);
+  CU(cudaMemcpyAsync(d_tf, b->time_fields, sizeof(int) * 6 * b->sim_len, cudaMemcpyHostToDevice, streams[0]));
+  if (b->forcing_mode == 1)
+    CU(cudaMemcpyAsync(d_rs, b->record_step, sizeof(int) * b->n_records, cudaMemcpyHostToDevice, streams[0]));
+  CU(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * RS_CNT_N, streams[0]));
+  CU(cudaStreamSynchronize(streams[0]));
+  sh.stats.h2d_bytes += sizeof(int) * (6 * b->sim_len + b->n_records);
+
+  for (int c = 0; c < nchunks; ++c)
+  {
+    const int s = c % NSTREAM;
+    cudaStream_t st = streams[s];
+    const int q0 = c * chunk;
+    const int npc = std::min(chunk, sh.count - q0);
+    const int ld = (npc + 31) / 32 * 32;
+    const size_t col0 = static_cast<size_t>(sh.first) + q0;
+    if (c >= NSTREAM)
+    {
+      // buffers of this stream are free once its previous chunk's D2H has finished
+      CU(cudaStreamSynchronize(st));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[s][0], ev[s][1]);
+      sh.stats.h2d_ms += ms;
+      cudaEventElapsedTime(&ms, ev[s][1], ev[s][2]);
+      sh.stats.kernel_ms += ms;
+      cudaEventElapsedTime(&ms, ev[s][2], ev[s][3]);
+      sh.stats.d2h_ms += ms;
+    }
+    const size_t wbytes = sizeof(double) * npc;
+    CU(cudaEventRecord(ev[s][0], st));
+    CU(cudaMemcpy2DAsync(d_forcing[s], sizeof(double) * ld, b->forcing + col0, sizeof(double) * np_all, wbytes,
+                         frows, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpy2DAsync(d_local[s], sizeof(double) * ld, b->local + col0, sizeof(double) * np_all, wbytes,
+                         RS_L_NLOCAL, cudaMemcpyHostToDevice, st));
+    if (hor)
+      CU(cudaMemcpy2DAsync(d_hor[s], sizeof(double) * ld, b->horizons + col0, sizeof(double) * np_all, wbytes, 360,
+                           cudaMemcpyHostToDevice, st));
+    sh.stats.h2d_bytes += wbytes * (frows + RS_L_NLOCAL + (hor ? 360 : 0));
+    CU(cudaEventRecord(ev[s][1], st));
+    RsArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.npoints = npc;
+    a.ld = ld;
+    a.sim_len = b->sim_len;
+    a.n_records = b->n_records;
+    a.nvar = b->nvar;
+    a.out_stride = b->out_stride;
+    a.n_out = n_out;
+    a.forcing_mode = b->forcing_mode;
+    a.forcing = d_forcing[s];
+    a.record_step = d_rs;
+    a.tf = d_tf;
+    a.local = d_local[s];
+    a.horizons = d_hor[s];
+    a.out = d_out[s];
+    a.status = d_status[s];
+    a.scratch = d_scratch[s];
+    a.counters = d_counters;
+    CU(static_cast<cudaError_t>(
+        rs_launch_run(&a, nl, st, &sh.launch.grid, &sh.launch.block, &sh.launch.regs_per_thread)));
+    ++sh.stats.kernel_launches;
+    sh.launch.nlayers = nl;
+    sh.launch.forcing_mode = b->forcing_mode;
+    CU(cudaEventRecord(ev[s][2], st));
+    CU(cudaMemcpy2DAsync(b->out + col0, sizeof(double) * np_all, d_out[s], sizeof(double) * ld, wbytes, orows,
+                         cudaMemcpyDeviceToHost, st));
+    if (b->status)
+      CU(cudaMemcpyAsync(b->status + col0, d_status[s], sizeof(int) * npc, cudaMemcpyDeviceToHost, st));
+    sh.stats.d2h_bytes += wbytes * orows + (b->status ? sizeof(int) * npc : 0);
+    CU(cudaEventRecord(ev[s][3], st));
+  }
+  for (int s = 0; s < NSTREAM && s < nchunks; ++s)
+  {
+    CU(cudaStreamSynchronize(streams[s]));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[s][0], ev[s][1]);
+    sh.stats.h2d_ms += ms;
+    cudaEventElapsedTime(&ms, ev[s][1], ev[s][2]);
+    sh.stats.kernel_ms += ms;
+    cudaEventElapsedTime(&ms, ev[s][2], ev[s][3]);
+    sh.stats.d2h_ms += ms;
+  }
+  unsigned long long cnt[RS_CNT_N];
+  CU(cudaMemcpy(cnt, d_counters, sizeof cnt, cudaMemcpyDeviceToHost));
+  sh.stats.executed_steps += static_cast<int64_t>(cnt[RS_CNT_EXECUTED_STEPS]);
+  sh.stats.groups = nchunks;
+  return RS_OK;
+}
+
+int run_sharded(int npoints, int ngpus, const std::function<int(Shard&)>& fn)
+{
+  const int ndev = roadsurf_device_count();
+  if (ndev < 1) return fail(RS_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
+  if (ngpus <= 0 || ngpus > ndev) ngpus = ndev;
+  if (ngpus > npoints) ngpus = npoints;
+  int current = 0;
+  cudaGetDevice(&current);
+  std::vector<Shard> shards(ngpus);
+  for (int g = 0; g < ngpus; ++g)
+  {
+    const long long a = static_cast<long long>(npoints) * g / ngpus;
+    const long long b = static_cast<long long>(npoints) * (g + 1) / ngpus;
+    shards[g].first = static_cast<int>(a);
+    shards[g].count = static_cast<int>(b - a);
+    shards[g].device = (ngpus == 1) ? current : g;
+  }
+  auto work = [&](int g) {
+    Shard& sh = shards[g];
+    sh.rc = fn(sh);
+    if (sh.rc != RS_OK) sh.err = g_err;
+  };
+  if (ngpus == 1)
+    work(0);
+  else
+  {
+    std::vector<std::thread> th;
+    for (int g = 0; g < ngpus; ++g) th.emplace_back(work, g);
+    for (auto& t : th) t.join();
+    cudaSetDevice(current);
+  }
+  for (auto& sh : shards)
+  {
+    g_stats.pack_ms = std::max(g_stats.pack_ms, sh.stats.pack_ms);
+    g_stats.h2d_ms = std::max(g_stats.h2d_ms, sh.stats.h2d_ms);
+    g_stats.kernel_ms = std::max(g_stats.kernel_ms, sh.stats.kernel_ms);
+    g_stats.d2h_ms = std::max(g_stats.d2h_ms, sh.stats.d2h_ms);
+    g_stats.unpack_ms = std::max(g_stats.unpack_ms, sh.stats.unpack_ms);
+    g_stats.h2d_bytes += sh.stats.h2d_bytes;
+    g_stats.d2h_bytes += sh.stats.d2h_bytes;
+    g_stats.executed_steps += sh.stats.executed_steps;
+    g_stats.kernel_launches += sh.stats.kernel_launches;
+    g_stats.groups += sh.stats.groups;
+    g_launches_total += sh.stats.kernel_launches;
+    if (sh.launch.grid) g_launch = sh.launch;
+  }
+  for (auto& sh : shards)
+    if (sh.rc != RS_OK) return fail(sh.rc, sh.err);
+  return RS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int roadsurf_run_host_soa(const RsHostBatch* b, const InputSettings* settings, const InputParameters* params,
+                          int ngpus)
+{
+  g_err.clear();
+  std::memset(&g_stats, 0, sizeof g_stats);
+  if (!b || !settings || !params) return fail(RS_ERR_BAD_ARGUMENT, "null argument");
+  if (b->npoints < 0 || b->sim_len < 1 || b->out_stride < 1) return fail(RS_ERR_BAD_ARGUMENT, "bad sizes");
+  if (b->sim_len != settings->SimLen) return fail(RS_ERR_BAD_ARGUMENT, "batch sim_len != settings SimLen");
+  if (b->nvar != RS_F_NVAR && b->nvar != RS_F_NVAR_DEPTH) return fail(RS_ERR_BAD_ARGUMENT, "nvar must be 11 or 12");
+  if (b->forcing_mode == 0 ? b->n_records != b->sim_len : (b->n_records < 2 || !b->record_step))
+    return fail(RS_ERR_BAD_ARGUMENT, "bad n_records / record_step for the forcing mode");
+  if (b->npoints > 0 && (!b->forcing || !b->time_fields || !b->local || !b->out))
+    return fail(RS_ERR_BAD_ARGUMENT, "null host pointer in batch");
+  if (b->npoints == 0) return roadsurf_device_count() < 1 ? fail(RS_ERR_NO_DEVICE, "no CUDA device visible") : RS_OK;
+  return run_sharded(b->npoints, ngpus, [&](Shard& sh) { return run_host_soa_shard(sh, b, settings, params); });
+}
+
+const char* roadsurf_last_error(void) { return g_err.c_str(); }
+
+const char* roadsurf_version(void) { return "roadsurf_b200 0.1 (RoadSurf 1.6.1 per-point loop, sm_100a)"; }
+
+int roadsurf_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int roadsurf_set_model(const InputSettings* settings, const InputParameters* params)
+{
+  if (!settings || !params) return fail(RS_ERR_BAD_ARGUMENT, "null settings/params");
+  if (roadsurf_device_count() < 1) return fail(RS_ERR_NO_DEVICE, "no CUDA device visible");
+  return set_model_on_current_device(settings, params, nullptr);
+}
+
+int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
+{
+  if (!b) return fail(RS_ERR_BAD_ARGUMENT, "null batch");
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  RsModel m;
+  {
+    std::lock_guard<std::mutex> lk(g_model_mu);
+    auto it = g_models.find(dev);
+    if (it == g_models.end()) return fail(RS_ERR_BAD_ARGUMENT, "roadsurf_set_model was not called on this device");
+    m = it->second;
+  }
+  if (b->ld < 32 || b->ld % 32 != 0 || b->npoints < 0 || b->npoints > b->ld)
+    return fail(RS_ERR_BAD_ARGUMENT, "ld must be a positive multiple of 32 and >= npoints");
+  if (b->sim_len < 1 || b->out_stride < 1 || b->n_out != (b->sim_len + b->out_stride - 1) / b->out_stride)
+    return fail(RS_ERR_BAD_ARGUMENT, "bad sim_len / out_stride / n_out");
+  if (b->nvar != RS_F_NVAR && b->nvar != RS_F_NVAR_DEPTH) return fail(RS_ERR_BAD_ARGUMENT, "nvar must be 11 or 12");
+  if (!b->forcing || !b->time_fields || !b->local || !b->out || !b->status)
+    return fail(RS_ERR_BAD_ARGUMENT, "null device pointer in batch");
+  if (b->forcing_mode == 0)
+  {
+    if (b->n_records != b->sim_len) return fail(RS_ERR_BAD_ARGUMENT, "forcing_mode 0 needs n_records == sim_len");
+  }
+  else if (b->forcing_mode == 1)
+  {
+    if (b->n_records < 2 || !b->record_step) return fail(RS_ERR_BAD_ARGUMENT, "coarse forcing needs >= 2 records");
+  }
+  else
+    return fail(RS_ERR_BAD_ARGUMENT, "forcing_mode must be 0 or 1");
+  if (m.use_coupling && !b->scratch) return fail(RS_ERR_BAD_ARGUMENT, "coupling needs batch->scratch");
+  RsArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.npoints = b->npoints;
+  a.ld = b->ld;
+  a.sim_len = b->sim_len;
+  a.n_records = b->n_records;
+  a.nvar = b->nvar;
+  a.out_stride = b->out_stride;
+  a.n_out = b->n_out;
+  a.forcing_mode = b->forcing_mode;
+  a.forcing = b->forcing;
+  a.record_step = b->record_step;
+  a.tf = b->time_fields;
+  a.local = b->local;
+  a.horizons = b->horizons;
+  a.out = b->out;
+  a.status = b->status;
+  a.state = b->state;
+  a.scratch = b->scratch;
+  a.counters = b->counters;
+  RsLaunchInfo li;
+  std::memset(&li, 0, sizeof li);
+  CU(static_cast<cudaError_t>(rs_launch_run(&a, m.nlayers, stream, &li.grid, &li.block, &li.regs_per_thread)));
+  li.nlayers = m.nlayers;
+  li.forcing_mode = b->forcing_mode;
+  li.launches_total = ++g_launches_total;
+  g_launch = li;
+  return RS_OK;
+}
+
+int roadsurf_transpose_to_soa(const double* src, int64_t src_ld, int npoints, int n, double* dst, int ld,
+                              void* stream)
+{
+  CU(static_cast<cudaError_t>(rs_launch_transpose_to_soa(src, src_ld, npoints, n, dst, ld, stream)));
+  ++g_launches_total;
+  return RS_OK;
+}
+
+int roadsurf_transpose_from_soa(const double* src, int ld, int npoints, int n, double* dst, int64_t dst_ld,
+                                void* stream)
+{
+  CU(static_cast<cudaError_t>(rs_launch_transpose_from_soa(src, ld, npoints, n, dst, dst_ld, stream)));
+  ++g_launches_total;
+  return RS_OK;
+}
+
+int roadsurf_fill(double* dst, int64_t n, double value, void* stream)
+{
+  CU(static_cast<cudaError_t>(rs_launch_fill(dst, n, value, stream)));
+  ++g_launches_total;
+  return RS_OK;
+}
+
+double roadsurf_measure_fp64_tflops(int iterations)
+{
+  if (roadsurf_device_count() < 1)
+  {
+    fail(RS_ERR_NO_DEVICE, "no CUDA device visible");
+    return -1.0;
+  }
+  return rs_measure_fp64(iterations > 0 ? iterations : 20000);
+}
+
+void roadsurf_last_launch(RsLaunchInfo* info)
+{
+  if (info)
+  {
+    *info = g_launch;
+    info->launches_total = g_launches_total;
+  }
+}
+
+void roadsurf_last_batch_stats(RsBatchStats* stats)
+{
+  if (stats) *stats = g_stats;
+}
+
+int roadsurf_run_batch(int npoints, OutputPointers* const* out, const InputPointers* const* in,
+                       const InputSettings* settings, const InputParameters* params,
+                       const LocalParameters* const* local, int ngpus, int* status)
+{
+  g_err.clear();
+  std::memset(&g_stats, 0, sizeof g_stats);
+  if (npoints < 0 || !settings || !params || (npoints > 0 && (!out || !in || !local)))
+    return fail(RS_ERR_BAD_ARGUMENT, "null argument");
+  if (roadsurf_device_count() < 1)
+    return fail(RS_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
+  if (npoints == 0) return RS_OK;
+  return run_sharded(npoints, ngpus,
+                     [&](Shard& sh) { return run_shard(sh, out, in, settings, params, local, status); });
+}
+
+void runsimulation(OutputPointers* outPointers, const InputPointers* inPointers, const InputSettings* inSettings,
+                   const InputParameters* inputParam, const LocalParameters* localParam)
+{
+  OutputPointers* outs[1] = {outPointers};
+  const InputPointers* ins[1] = {inPointers};
+  const LocalParameters* locs[1] = {localParam};
+  const int rc = roadsurf_run_batch(1, outs, ins, inSettings, inputParam, locs, 1, nullptr);
+  if (rc != RS_OK)
+  {
+    // The reference signature has no error channel: report and leave the outputs at -9999.0,
+    // which is how the reference marks "not computed" (src/Initialization.f90:397-412).
+    std::fprintf(stderr, "roadsurf_b200 runsimulation failed: %s\n", roadsurf_last_error());
+    if (outPointers && inSettings)
+    {
+      double* o[RS_O_NVAR] = {outPointers->c_TsurfOut, outPointers->c_SnowOut,    outPointers->c_WaterOut,
+                              outPointers->c_IceOut,   outPointers->c_DepositOut, outPointers->c_Ice2Out};
+      for (int v = 0; v < RS_O_NVAR; ++v)
+        if (o[v])
+          for (int t = 0; t < inSettings->SimLen && t < outPointers->outputLen; ++t) o[v][t] = -9999.0;
+    }
+  }
+}
+
+}  // extern "C"

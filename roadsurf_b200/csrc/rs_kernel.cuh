@@ -1,0 +1,42 @@
+// rs_kernel.cuh -- launch arguments shared by the kernels and the host code.
+#pragma once
+
+#include "rs_model.h"
+
+// Device scratch planes needed when coupling is in use (fp64 planes of `ld` points):
+//   [0, N+1]      Tmp(0:N+1) snapshot at the start of the coupling window  (src/Coupling.f90:172-210)
+//   N+2 .. N+7    TsurfAve, SrfWatmms, SrfIce2mms, SrfDepmms, SrfSnowmms, Albedo snapshot
+//   N+9 .. 2N+8   TmpNw(1:N) of the pass that just ended (read by the first re-run step only)
+//   2N+9 .. 2N+15 RadCoeff, RadCoeffPrevious, TsurfNearestAbove/Below, RadCoefNearestAbove/Below,
+//                 Tsurf_end_coup1 (touched once per coupling pass)
+
+struct RsArgs
+{
+  int npoints, ld, sim_len, n_records, nvar, out_stride, n_out, forcing_mode;
+  const double* forcing;
+  const int* record_step;
+  const int* tf;            // [6][sim_len]
+  const double* local;      // [RS_L_NLOCAL][ld]
+  const double* horizons;   // [360][ld] or null
+  double* out;              // [6][n_out][ld]
+  int* status;
+  double* state;
+  double* scratch;          // [RS_SCRATCH_NPLANES(N)][ld] or null
+  unsigned long long* counters;
+};
+
+#define RS_BLOCK 128
+
+// Host-callable launchers (rs_kernel.cu).  Return a cudaError_t as int.
+int rs_upload_model(const RsModel* m);
+int rs_launch_run(const RsArgs* a, int nlayers, void* stream, int* grid, int* block, int* regs);
+int rs_launch_transpose_to_soa(const double* src, long long src_ld, int npoints, int n, double* dst,
+                               int ld, void* stream);
+int rs_launch_transpose_from_soa(const double* src, int ld, int npoints, int n, double* dst,
+                                 long long dst_ld, void* stream);
+int rs_launch_fill(double* dst, long long n, double value, void* stream);
+int rs_launch_pack_forcing(const double* stage, int npoints_chunk, int p0, int sim_len, int nvar,
+                           double* forcing, int ld, void* stream);
+int rs_launch_unpack_out(const double* out, int ld, int n_out, int p0, int npoints_chunk,
+                         double* stage, void* stream);
+double rs_measure_fp64(int iterations);

@@ -1,0 +1,291 @@
+"""ctypes binding of libroadsurf_b200.so (the C ABI declared in include/roadsurf_b200.h).
+
+The library is the product; this module only loads it and marshals arguments.  There is no Python
+or CPU implementation of the model behind these calls: if the shared library is missing, or no
+CUDA device is visible, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libroadsurf_b200.so")
+
+# enums of include/roadsurf_b200.h
+ST_FAILED, ST_BAD_INPUT, ST_ABNORMAL_TSURF, ST_COUPLING_USED, ST_COUPLING_FAILED = 1, 2, 4, 8, 16
+ST_BL_NOT_CONVERGED, ST_SOLAR_GEOMETRY, ST_BAD_WINDOW, ST_NOT_RUN = 32, 64, 128, 256
+F_NVAR, F_NVAR_DEPTH = 11, 12
+F_NAMES = ("tair", "tdew", "VZ", "Rhz", "prec", "SW", "LW", "SW_dir", "LW_net", "TSurfObs", "PrecPhase",
+           "Depth")
+(L_TAIR_RELAX, L_VZ_RELAX, L_RH_RELAX, L_COUPLING_TSURF, L_LAT, L_LON, L_SKY_VIEW, L_COUPLING_INDEX,
+ L_INIT_LEN, L_ACTIVE, L_NLOCAL) = range(11)
+O_NAMES = ("TsurfOut", "SnowOut", "WaterOut", "IceOut", "DepositOut", "Ice2Out")
+O_NVAR = 6
+CNT_EXECUTED_STEPS, CNT_BL_ITERATIONS, CNT_COUPLING_PASSES, CNT_FAILED_POINTS, CNT_N = 0, 1, 2, 3, 8
+
+EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roadsurf_run_batch",
+           "roadsurf_run_host_soa",
+           "roadsurf_last_batch_stats", "roadsurf_set_model", "roadsurf_run_device",
+           "roadsurf_transpose_to_soa", "roadsurf_transpose_from_soa", "roadsurf_fill",
+           "roadsurf_measure_fp64_tflops", "roadsurf_last_launch", "roadsurf_version")
+
+
+def state_nplanes(nlayers):
+    return nlayers + 2 + 12
+
+
+def scratch_nplanes(nlayers):
+    return 2 * nlayers + 16
+
+
+class RsBatchStats(C.Structure):
+    _fields_ = [("pack_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double),
+                ("d2h_ms", C.c_double), ("unpack_ms", C.c_double), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("executed_steps", C.c_int64), ("kernel_launches", C.c_int),
+                ("groups", C.c_int)]
+
+
+class RsLaunchInfo(C.Structure):
+    _fields_ = [("grid", C.c_int), ("block", C.c_int), ("smem_bytes", C.c_int),
+                ("regs_per_thread", C.c_int), ("nlayers", C.c_int), ("forcing_mode", C.c_int),
+                ("launches_total", C.c_int)]
+
+
+class RsDeviceBatch(C.Structure):
+    _fields_ = [("npoints", C.c_int), ("ld", C.c_int), ("sim_len", C.c_int), ("forcing_mode", C.c_int),
+                ("n_records", C.c_int), ("nvar", C.c_int),
+                ("forcing", C.c_void_p), ("record_step", C.c_void_p), ("time_fields", C.c_void_p),
+                ("local", C.c_void_p), ("horizons", C.c_void_p), ("out", C.c_void_p),
+                ("out_stride", C.c_int), ("n_out", C.c_int), ("status", C.c_void_p),
+                ("state", C.c_void_p), ("scratch", C.c_void_p), ("counters", C.c_void_p)]
+
+
+class RsHostBatch(C.Structure):
+    _fields_ = [("npoints", C.c_int), ("sim_len", C.c_int), ("forcing_mode", C.c_int), ("n_records", C.c_int),
+                ("nvar", C.c_int), ("out_stride", C.c_int),
+                ("forcing", C.c_void_p), ("record_step", C.c_void_p), ("time_fields", C.c_void_p),
+                ("local", C.c_void_p), ("horizons", C.c_void_p), ("out", C.c_void_p), ("status", C.c_void_p)]
+
+
+class RoadSurfError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libroadsurf_b200.so; raises if it has not been built (see roadsurf_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RoadSurfError(f"{LIB_PATH} is missing: run `python -m roadsurf_b200.build` "
+                            "(there is no fallback implementation)")
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    OP, IP, IS, IPa, LP = (abi.OutputPointers, abi.InputPointers, abi.InputSettings, abi.InputParameters,
+                           abi.LocalParameters)
+    lib.runsimulation.argtypes = [P(OP), P(IP), P(IS), P(IPa), P(LP)]
+    lib.runsimulation.restype = None
+    lib.roadsurf_last_error.restype = C.c_char_p
+    lib.roadsurf_version.restype = C.c_char_p
+    lib.roadsurf_device_count.restype = C.c_int
+    lib.roadsurf_run_batch.argtypes = [C.c_int, P(P(OP)), P(P(IP)), P(IS), P(IPa), P(P(LP)), C.c_int,
+                                       P(C.c_int)]
+    lib.roadsurf_run_batch.restype = C.c_int
+    lib.roadsurf_run_host_soa.argtypes = [P(RsHostBatch), P(IS), P(IPa), C.c_int]
+    lib.roadsurf_run_host_soa.restype = C.c_int
+    lib.roadsurf_last_batch_stats.argtypes = [P(RsBatchStats)]
+    lib.roadsurf_set_model.argtypes = [P(IS), P(IPa)]
+    lib.roadsurf_set_model.restype = C.c_int
+    lib.roadsurf_run_device.argtypes = [P(RsDeviceBatch), C.c_void_p]
+    lib.roadsurf_run_device.restype = C.c_int
+    lib.roadsurf_transpose_to_soa.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                              C.c_void_p]
+    lib.roadsurf_transpose_to_soa.restype = C.c_int
+    lib.roadsurf_transpose_from_soa.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                                C.c_void_p]
+    lib.roadsurf_transpose_from_soa.restype = C.c_int
+    lib.roadsurf_fill.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
+    lib.roadsurf_fill.restype = C.c_int
+    lib.roadsurf_measure_fp64_tflops.argtypes = [C.c_int]
+    lib.roadsurf_measure_fp64_tflops.restype = C.c_double
+    lib.roadsurf_last_launch.argtypes = [P(RsLaunchInfo)]
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RoadSurfError(f"roadsurf_b200 error {rc}: {load().roadsurf_last_error().decode()}")
+
+
+def last_batch_stats():
+    st = RsBatchStats()
+    load().roadsurf_last_batch_stats(C.byref(st))
+    return {n: getattr(st, n) for n, _ in RsBatchStats._fields_}
+
+
+def last_launch():
+    li = RsLaunchInfo()
+    load().roadsurf_last_launch(C.byref(li))
+    return {n: getattr(li, n) for n, _ in RsLaunchInfo._fields_}
+
+
+def run_batch(arrays, settings, params, ngpus=1):
+    """roadsurf_run_batch over a host-layout PointArrays: fills arrays.out, returns status[npoints]."""
+    lib = load()
+    ins = arrays.input_pointers()
+    outs = arrays.output_pointers()
+    in_ptrs = abi.pointer_arrays(ins, abi.InputPointers)
+    out_ptrs = abi.pointer_arrays(outs, abi.OutputPointers)
+    loc_ptrs = abi.pointer_arrays(arrays.local, abi.LocalParameters)
+    status = np.zeros(arrays.npoints, dtype=np.int32)
+    _check(lib.roadsurf_run_batch(arrays.npoints, out_ptrs, in_ptrs, C.byref(settings), C.byref(params),
+                                  loc_ptrs, int(ngpus), status.ctypes.data_as(abi.c_int_p)))
+    return status
+
+
+def run_host_soa(settings, params, forcing, time_fields, local, out, record_step=None, horizons=None,
+                 status=None, out_stride=1, ngpus=1):
+    """roadsurf_run_host_soa on host tensors/arrays (torch CPU tensors -- ideally pinned -- or numpy):
+    forcing [n_records, nvar, npoints] f64, time_fields [6, sim_len] i32, local [L_NLOCAL, npoints],
+    out [6, n_out, npoints] (written), record_step [n_records] i32 for coarse forcing."""
+    def ptr(x):
+        if x is None:
+            return None
+        return x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
+    n_records, nvar, npoints = forcing.shape
+    sim_len = time_fields.shape[1]
+    n_out = (sim_len + out_stride - 1) // out_stride
+    assert tuple(out.shape) == (O_NVAR, n_out, npoints) and tuple(local.shape) == (L_NLOCAL, npoints)
+    hb = RsHostBatch(npoints=npoints, sim_len=sim_len, forcing_mode=0 if record_step is None else 1,
+                     n_records=n_records, nvar=nvar, out_stride=out_stride, forcing=ptr(forcing),
+                     record_step=ptr(record_step), time_fields=ptr(time_fields), local=ptr(local),
+                     horizons=ptr(horizons), out=ptr(out), status=ptr(status))
+    _check(load().roadsurf_run_host_soa(C.byref(hb), C.byref(settings), C.byref(params), int(ngpus)))
+
+
+def runsimulation(arrays, settings, params, point=0):
+    """The reference's single-point entry, through the exact reference signature."""
+    lib = load()
+    ins = arrays.input_pointers()
+    outs = arrays.output_pointers()
+    lib.runsimulation(C.byref(outs[point]), C.byref(ins[point]), C.byref(settings), C.byref(params),
+                      C.byref(arrays.local[point]))
+
+
+class DeviceBatch:
+    """Device-resident structure-of-arrays batch (RsDeviceBatch) backed by torch CUDA tensors.
+
+    torch is used for device memory and streams only.  Layouts (point index fastest, `ld` padded to
+    a multiple of 32): forcing [n_records, nvar, ld], local [L_NLOCAL, ld], horizons [360, ld],
+    out [6, n_out, ld], status [ld]."""
+
+    def __init__(self, npoints, sim_len, nlayers=15, n_records=None, nvar=F_NVAR, out_stride=1,
+                 coarse=False, horizons=False, coupling=False, state=False, device="cuda"):
+        import torch
+        self.torch = torch
+        self.npoints, self.sim_len, self.nlayers = int(npoints), int(sim_len), int(nlayers)
+        self.ld = (self.npoints + 31) // 32 * 32
+        self.coarse = bool(coarse)
+        self.n_records = int(n_records) if coarse else self.sim_len
+        self.nvar = int(nvar)
+        self.out_stride = int(out_stride)
+        self.n_out = (self.sim_len + self.out_stride - 1) // self.out_stride
+        f64 = dict(dtype=torch.float64, device=device)
+        self.forcing = torch.zeros((self.n_records, self.nvar, self.ld), **f64)
+        self.record_step = torch.zeros(self.n_records, dtype=torch.int32, device=device) if coarse else None
+        self.time_fields = torch.zeros((6, self.sim_len), dtype=torch.int32, device=device)
+        self.local = torch.zeros((L_NLOCAL, self.ld), **f64)
+        self.local[L_SKY_VIEW].fill_(1.0)
+        self.local[L_ACTIVE, :self.npoints] = 1.0
+        self.local[L_COUPLING_TSURF].fill_(-9999.0)
+        self.local[L_COUPLING_INDEX].fill_(-9999.0)
+        self.local[L_TAIR_RELAX:L_RH_RELAX + 1].fill_(-9999.0)
+        self.horizons = torch.zeros((360, self.ld), **f64) if horizons else None
+        self.out = torch.empty((O_NVAR, self.n_out, self.ld), **f64)
+        self.status = torch.zeros(self.ld, dtype=torch.int32, device=device)
+        self.state = torch.zeros((state_nplanes(nlayers), self.ld), **f64) if state else None
+        self.scratch = torch.zeros((scratch_nplanes(nlayers), self.ld), **f64) if coupling else None
+        self.counters = torch.zeros(CNT_N, dtype=torch.int64, device=device)
+
+    def descriptor(self):
+        def ptr(t):
+            return None if t is None else t.data_ptr()
+        return RsDeviceBatch(npoints=self.npoints, ld=self.ld, sim_len=self.sim_len,
+                             forcing_mode=1 if self.coarse else 0, n_records=self.n_records,
+                             nvar=self.nvar, forcing=ptr(self.forcing), record_step=ptr(self.record_step),
+                             time_fields=ptr(self.time_fields), local=ptr(self.local),
+                             horizons=ptr(self.horizons), out=ptr(self.out), out_stride=self.out_stride,
+                             n_out=self.n_out, status=ptr(self.status), state=ptr(self.state),
+                             scratch=ptr(self.scratch), counters=ptr(self.counters))
+
+    def run(self, stream=None):
+        """Asynchronous launch on `stream` (a torch.cuda.Stream; default: the current stream)."""
+        st = stream if stream is not None else self.torch.cuda.current_stream()
+        desc = self.descriptor()
+        _check(load().roadsurf_run_device(C.byref(desc), C.c_void_p(st.cuda_stream)))
+
+    # ---- helpers to fill the batch from host-layout data (tests, small cases) -----------------
+    def load_point_arrays(self, arrays):
+        """Full-resolution forcing + statics from a host-layout PointArrays (numpy side transpose;
+        only used by tests and smoke, the batched C entry point has its own device pack path)."""
+        torch = self.torch
+        assert not self.coarse and arrays.sim_len == self.sim_len and arrays.npoints == self.npoints
+        host = np.zeros((self.sim_len, self.nvar, self.ld))
+        for v in range(self.nvar):
+            src = getattr(arrays, F_NAMES[v])
+            host[:, v, :self.npoints] = src.T
+        self.forcing.copy_(torch.from_numpy(host))
+        self.time_fields.copy_(torch.from_numpy(arrays.time))
+        self.load_local(arrays.local, arrays.local_horizons)
+
+    def load_local(self, local, horizons=None):
+        torch = self.torch
+        n = self.npoints
+        L = np.zeros((L_NLOCAL, self.ld))
+        L[L_SKY_VIEW] = 1.0
+        L[L_COUPLING_TSURF] = L[L_COUPLING_INDEX] = -9999.0
+        for p in range(n):
+            lp = local[p]
+            L[:, p] = (lp.tair_relax, lp.VZ_relax, lp.RH_relax, lp.couplingTsurf, lp.lat, lp.lon,
+                       lp.sky_view, lp.couplingIndexI, lp.InitLenI, 1.0)
+        self.local.copy_(torch.from_numpy(L))
+        if self.horizons is not None and horizons is not None:
+            H = np.zeros((360, self.ld))
+            H[:, :n] = np.asarray(horizons).T
+            self.horizons.copy_(torch.from_numpy(H))
+
+    def load_records(self, rec):
+        """Coarse forcing records (synth.Records) + statics."""
+        torch = self.torch
+        assert self.coarse and rec.nrec == self.n_records
+        host = np.zeros((self.n_records, self.nvar, self.ld))
+        names = ("tair", "tdew", "VZ", "Rhz", "prec", "SW", "LW", "SW_dir", "LW_net", "TSurfObs", "PrecPhase")
+        for v, name in enumerate(names):
+            host[:, v, :self.npoints] = getattr(rec, name).T
+        if self.nvar > F_NVAR:
+            host[:, F_NVAR, :] = -9999.9
+        self.forcing.copy_(torch.from_numpy(host))
+        self.record_step.copy_(torch.from_numpy(rec.record_step.astype(np.int32)))
+
+    def outputs(self):
+        """dict name -> numpy [npoints, n_out]."""
+        o = self.out.cpu().numpy()
+        return {name: np.ascontiguousarray(o[v, :, :self.npoints].T) for v, name in enumerate(O_NAMES)}
+
+
+def set_model(settings, params):
+    _check(load().roadsurf_set_model(C.byref(settings), C.byref(params)))
+
+
+def measure_fp64_tflops(iterations=20000):
+    v = load().roadsurf_measure_fp64_tflops(int(iterations))
+    if v < 0:
+        raise RoadSurfError(load().roadsurf_last_error().decode())
+    return v

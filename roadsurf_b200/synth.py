@@ -65,6 +65,7 @@ class Records:
         self.sky_view = np.ones(npoints)
         self.horizons = np.zeros((npoints, 360))
         self.record_step = np.zeros(nrec, dtype=np.int32)  # 0-based model step of every record
+        self.obs_bias = None  # optional [npoints, 3]: analysis-period offsets of tair, VZ, Rhz
 
 
 def draw_records(npoints, nrec, seed, start, record_secs=3600, dt_secs=30.0, first_step=0,
@@ -128,17 +129,18 @@ def draw_records(npoints, nrec, seed, start, record_secs=3600, dt_secs=30.0, fir
     return r
 
 
-def interpolate_records(rec, sim_len):
+def interpolate_records(rec, sim_len, dt_secs=30.0):
     """Records -> per-step arrays, following JsonSource.cpp:49-176 for a record grid that starts
-    at or before step 0 and extends beyond the last step.  Returns dict name -> [npoints, sim_len]
-    (PrecPhase as int32)."""
+    at or before step 0 and extends beyond the last step.  Times are integer seconds there, so the
+    weights are formed from seconds, not steps (the rounding differs).  Returns dict name ->
+    [npoints, sim_len] (PrecPhase as int32)."""
     steps = np.arange(sim_len, dtype=np.int64)
     rs = rec.record_step.astype(np.int64)
     if rs[0] > 0 or rs[-1] <= sim_len - 1:
         raise ValueError("records must bracket the simulation (first <= step 0, last > last step)")
     k = np.searchsorted(rs, steps, side="right") - 1  # rs[k] <= step < rs[k+1]
-    dt_a = (steps - rs[k]).astype(np.float64)
-    span = (rs[k + 1] - rs[k]).astype(np.float64)
+    dt_a = (steps - rs[k]).astype(np.float64) * dt_secs
+    span = (rs[k + 1] - rs[k]).astype(np.float64) * dt_secs
     exact = (steps == rs[k])
     out = {}
     for v in RECORD_VARS:
@@ -191,43 +193,34 @@ def read_input_derive(arrays, settings, forecast_step):
                 obs[i - span + 1:i + 1] = -9999.9
 
 
-def make_case(npoints, hours, seed, analysis_hours=0, use_coupling=0, use_relaxation=0,
-              dt=30.0, nlayers=15, start=None, sky_view_fraction=0.3, obs_bias=True, **kw):
-    """Full-resolution host-layout case: (PointArrays, InputSettings, InputParameters, Records).
-
-    The simulation starts `analysis_hours` before `start` (default FORECAST_START) and runs
-    `hours` of forecast: SimLen = 1 + (analysis_hours + hours) * 3600 / dt."""
+def case_from_records(rec, hours, analysis_hours=0, use_coupling=0, use_relaxation=0, dt=30.0, nlayers=15,
+                      start=None, **settings_kw):
+    """Full-resolution host-layout case built deterministically (no random numbers) from coarse
+    records: (PointArrays, InputSettings, InputParameters)."""
     start = start or FORECAST_START
+    npoints = rec.npoints
     per_hour = int(round(3600.0 / dt))
     sim_len = 1 + (analysis_hours + hours) * per_hour
     sim_start = start - _dt.timedelta(hours=analysis_hours)
-    nrec = analysis_hours + hours + 2
-    rec = draw_records(npoints, nrec, seed, sim_start, 3600, dt, 0, sky_view_fraction, **kw)
     forecast_step = analysis_hours * per_hour
-    if analysis_hours > 0:
-        # observations exist up to forecast start; none afterwards
-        rec.TSurfObs[:, analysis_hours + 1:] = -9999.9
-    else:
-        rec.TSurfObs[:, :] = -9999.9
-    fields = interpolate_records(rec, sim_len)
+    fields = interpolate_records(rec, sim_len, dt)
     pa = abi.PointArrays(npoints, sim_len)
     for v in RECORD_VARS:
         if v == "PrecPhase":
             pa.PrecPhase[:] = fields[v]
         else:
             getattr(pa, v)[:] = fields[v]
-    if analysis_hours > 0 and obs_bias:
+    if analysis_hours > 0 and rec.obs_bias is not None:
         # observed atmosphere differs from the forecast one during the analysis: a jump that the
         # relaxation phase has to smooth (src/Relaxation.f90)
-        rng = np.random.Generator(np.random.PCG64(seed + 77))
         n_obs = forecast_step + 1
-        pa.tair[:, :n_obs] += rng.normal(0.0, 1.0, (npoints, 1))
-        pa.VZ[:, :n_obs] = np.clip(pa.VZ[:, :n_obs] + rng.normal(0.0, 0.7, (npoints, 1)), 0.0, 25.0)
-        pa.Rhz[:, :n_obs] = np.clip(pa.Rhz[:, :n_obs] + rng.normal(0.0, 4.0, (npoints, 1)), 35.0, 100.0)
+        pa.tair[:, :n_obs] += rec.obs_bias[:, [0]]
+        pa.VZ[:, :n_obs] = np.clip(pa.VZ[:, :n_obs] + rec.obs_bias[:, [1]], 0.0, 25.0)
+        pa.Rhz[:, :n_obs] = np.clip(pa.Rhz[:, :n_obs] + rec.obs_bias[:, [2]], 35.0, 100.0)
         pa.TSurfObs[:, n_obs:] = -9999.9
     pa.local_horizons[:] = rec.horizons
     pa.time[:] = time_axis(sim_start, sim_len, dt)
-    settings = abi.default_settings(sim_len, use_coupling, use_relaxation, dt, nlayers)
+    settings = abi.default_settings(sim_len, use_coupling, use_relaxation, dt, nlayers, **settings_kw)
     params = abi.default_parameters(dt)
     for p in range(npoints):
         lp = pa.local[p]
@@ -237,4 +230,29 @@ def make_case(npoints, hours, seed, analysis_hours=0, use_coupling=0, use_relaxa
         lp.lat, lp.lon, lp.sky_view = rec.lat[p], rec.lon[p], rec.sky_view[p]
         lp.InitLenI = 0
     read_input_derive(pa, settings, forecast_step)
+    return pa, settings, params
+
+
+def make_case(npoints, hours, seed, analysis_hours=0, use_coupling=0, use_relaxation=0,
+              dt=30.0, nlayers=15, start=None, sky_view_fraction=0.3, obs_bias=True, settings_kw=None,
+              **kw):
+    """Seeded full-resolution host-layout case: (PointArrays, InputSettings, InputParameters, Records).
+
+    The simulation starts `analysis_hours` before `start` (default FORECAST_START) and runs
+    `hours` of forecast: SimLen = 1 + (analysis_hours + hours) * 3600 / dt."""
+    start = start or FORECAST_START
+    sim_start = start - _dt.timedelta(hours=analysis_hours)
+    nrec = analysis_hours + hours + 2
+    rec = draw_records(npoints, nrec, seed, sim_start, 3600, dt, 0, sky_view_fraction, **kw)
+    if analysis_hours > 0:
+        # observations exist up to forecast start; none afterwards
+        rec.TSurfObs[:, analysis_hours + 1:] = -9999.9
+        if obs_bias:
+            rng = np.random.Generator(np.random.PCG64(seed + 77))
+            rec.obs_bias = np.stack([rng.normal(0.0, 1.0, npoints), rng.normal(0.0, 0.7, npoints),
+                                     rng.normal(0.0, 4.0, npoints)], axis=1)
+    else:
+        rec.TSurfObs[:, :] = -9999.9
+    pa, settings, params = case_from_records(rec, hours, analysis_hours, use_coupling, use_relaxation, dt,
+                                             nlayers, start, **(settings_kw or {}))
     return pa, settings, params, rec

@@ -1,0 +1,301 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (roadsurf_run_batch,
+runsimulation, roadsurf_run_device).  All tests need a GPU.
+
+Tolerances are BASELINE.json's: temperatures within 1e-3 K, storages within 1e-3 mm; points whose
+trajectories separate at a threshold (freeze/melt limits, minimum storages) are counted as the
+mismatch fraction and must stay rare and bounded.  Point indexing, the -9999.0 fill and the status
+words are compared exactly.
+"""
+import numpy as np
+import pytest
+
+from golden_io import CASE_NAMES, load_case
+from parity import S_TOL, T_TOL, compare
+from roadsurf_b200 import abi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(rslib, oracle, arrays, settings, params, ngpus=1):
+    ref = arrays.copy()
+    st_gpu = rslib.run_batch(arrays, settings, params, ngpus=ngpus)
+    st_cpu, steps = oracle.run_batch(ref, settings, params, nthreads=8)
+    return compare(arrays.out, ref.out), st_gpu, st_cpu, ref, steps
+
+
+def _assert_parity(r, max_mismatch=0.05):
+    assert r["max_dT_matching"] <= T_TOL, r
+    assert r["max_dS_matching"] <= S_TOL, r
+    assert r["mismatch_fraction"] <= max_mismatch, r
+    # a flipped point stays close: one wear/melt quantum, not a different regime
+    assert r["max_dT_all"] < 0.5 and r["max_dS_all"] < 0.5, r
+
+
+def test_plain_forecast_matches_oracle(rslib, oracle):
+    """c2-like: multi-point, no coupling, 30 % of the points with sky-view radiation."""
+    arrays, settings, params, _ = synth.make_case(300, 24, seed=21)
+    r, sg, sc, ref, steps = _run_both(rslib, oracle, arrays, settings, params)
+    _assert_parity(r)
+    assert np.array_equal(sg, sc)
+    stats = rslib.last_batch_stats()
+    assert stats["executed_steps"] == steps == 300 * arrays.sim_len
+    assert rslib.last_launch()["regs_per_thread"] > 0
+
+
+def test_coupling_and_relaxation_match_oracle(rslib, oracle):
+    """c3-like: 6 h analysis + 24 h forecast with coupling to the last observation + relaxation."""
+    arrays, settings, params, _ = synth.make_case(400, 24, seed=22, analysis_hours=6, use_coupling=1,
+                                                   use_relaxation=1)
+    r, sg, sc, ref, steps = _run_both(rslib, oracle, arrays, settings, params)
+    _assert_parity(r)
+    assert np.array_equal(sg, sc) and (sg & rslib.ST_COUPLING_USED).all()
+    # coupling did its job: surface temperature at the window end is near the observation
+    end = arrays.local[0].couplingIndexI - 1
+    ok = ~((sg & rslib.ST_COUPLING_FAILED) > 0)
+    obs = np.array([arrays.local[p].couplingTsurf for p in range(arrays.npoints)])
+    assert np.max(np.abs(arrays.out["TsurfOut"][ok, end] - obs[ok])) < 0.11
+    # the lockstep re-runs cost more steps than the per-point re-runs, never fewer
+    assert rslib.last_batch_stats()["executed_steps"] == steps
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_golden_fixtures(rslib, name):
+    arrays, settings, params, golden, status, stride, steps = load_case(name)
+    st = rslib.run_batch(arrays, settings, params, ngpus=1)
+    assert np.array_equal(st, status)
+    got = {k: arrays.out[k][:, ::stride] for k in golden}
+    _assert_parity(compare(got, golden), max_mismatch=0.34)
+
+
+def test_runsimulation_single_point_drop_in(rslib, oracle):
+    """The reference's own entry point and signature (examples/example1/src/Simulation.f90:4-6)."""
+    arrays, settings, params, _ = synth.make_case(3, 6, seed=23, analysis_hours=6, use_coupling=1,
+                                                   use_relaxation=1, sky_view_fraction=1.0)
+    ref = arrays.copy()
+    for p in range(3):
+        rslib.runsimulation(arrays, settings, params, point=p)
+    oracle.run_batch(ref, settings, params)
+    _assert_parity(compare(arrays.out, ref.out), max_mismatch=0.34)
+
+
+def test_empty_ragged_and_tiny_batches(rslib, oracle):
+    arrays, settings, params, _ = synth.make_case(1, 1, seed=24)
+    empty = abi.PointArrays(0, arrays.sim_len)
+    assert len(rslib.run_batch(empty, settings, params)) == 0          # npoints = 0
+    for npts in (1, 31, 33, 97):                                       # not multiples of the warp size
+        arrays, settings, params, _ = synth.make_case(npts, 2, seed=25 + npts)
+        r, sg, sc, _, _ = _run_both(rslib, oracle, arrays, settings, params)
+        _assert_parity(r, max_mismatch=0.2)
+        assert np.array_equal(sg, sc)
+    # SimLen = 1 (only the "last value" step runs) and SimLen = 2
+    for sim_len in (1, 2):
+        arrays, settings, params, _ = synth.make_case(5, 1, seed=26)
+        settings.SimLen = sim_len
+        short = abi.PointArrays(5, sim_len)
+        for n in abi.INPUT_DOUBLE_FIELDS:
+            getattr(short, n[2:])[:] = getattr(arrays, n[2:])[:, :sim_len]
+        short.PrecPhase[:] = arrays.PrecPhase[:, :sim_len]
+        short.time[:] = arrays.time[:, :sim_len]
+        short.local_horizons[:] = arrays.local_horizons
+        for p in range(5):
+            short.local[p] = arrays.local[p]
+        r, sg, sc, _, _ = _run_both(rslib, oracle, short, settings, params)
+        assert r["max_dT_all"] < 1e-9 and r["max_dS_all"] < 1e-9 and np.array_equal(sg, sc)
+
+
+def test_bad_input_stops_the_point_and_leaves_missing_values(rslib, oracle):
+    """CheckValues (src/InputOutput.f90:45-84): the loop stops, later outputs stay -9999.0."""
+    arrays, settings, params, _ = synth.make_case(40, 6, seed=27)
+    arrays.tair[3, 100] = 150.0       # out of range at step 101
+    arrays.VZ[7, 0] = -5.0            # clamped to 0.4 by Initialization before it is checked
+    arrays.SW[9, 300] = np.nan        # NaN compares false: not caught by the range check
+    arrays.Rhz[11, 1] = 130.0
+    r, sg, sc, ref, _ = _run_both(rslib, oracle, arrays, settings, params)
+    assert np.array_equal(sg, sc)
+    assert sg[3] & rslib.ST_FAILED and sg[3] & rslib.ST_BAD_INPUT and sg[11] & rslib.ST_FAILED
+    assert not (sg[7] & rslib.ST_FAILED)
+    for k in arrays.out:
+        # identical pattern of computed / missing values, bit-exact fill
+        assert np.array_equal(arrays.out[k] == -9999.0, ref.out[k] == -9999.0), k
+        assert np.array_equal(np.isnan(arrays.out[k]), np.isnan(ref.out[k])), k
+    assert (arrays.out["TsurfOut"][3, 101:] == -9999.0).all() and arrays.out["TsurfOut"][3, 100] != -9999.0
+    assert (arrays.out["TsurfOut"][11, 2:] == -9999.0).all()
+    good = [p for p in range(40) if p not in (3, 9, 11)]
+    sub = lambda o: {k: v[good] for k, v in o.items()}
+    _assert_parity(compare(sub(arrays.out), sub(ref.out)), max_mismatch=0.2)
+
+
+def test_missing_observations_and_mixed_coupling_windows(rslib, oracle):
+    """Per-point coupling windows: different observation times, points without observations and
+    points whose window starts at step 1 share one batch (grouped into warps by the library)."""
+    arrays, settings, params, _ = synth.make_case(150, 6, seed=28, analysis_hours=6, use_coupling=1,
+                                                   use_relaxation=1)
+    rng = np.random.default_rng(5)
+    for p in range(150):
+        lp = arrays.local[p]
+        kind = p % 5
+        if kind == 1:                                   # no surface observation: coupling off
+            lp.couplingTsurf, lp.couplingIndexI = -9999.9, -9999
+        elif kind == 2:                                 # earlier observation time
+            lp.couplingIndexI = int(rng.integers(400, 700))
+        elif kind == 3:                                 # window clipped at the start of the run
+            lp.couplingIndexI = int(rng.integers(50, 360))
+        elif kind == 4:                                 # relaxation switched off by a bad target
+            lp.tair_relax = -9999.9
+    r, sg, sc, ref, steps = _run_both(rslib, oracle, arrays, settings, params)
+    assert np.array_equal(sg, sc)
+    assert not (sg[1::5] & rslib.ST_COUPLING_USED).any() and (sg[0::5] & rslib.ST_COUPLING_USED).all()
+    _assert_parity(r, max_mismatch=0.1)
+    assert rslib.last_batch_stats()["groups"] == 1
+
+
+def test_time_axis_per_point_is_grouped(rslib, oracle):
+    arrays, settings, params, _ = synth.make_case(70, 3, seed=29, sky_view_fraction=1.0)
+    import datetime as dt
+    tpp = np.repeat(arrays.time[None], 70, axis=0).copy()
+    summer = synth.time_axis(dt.datetime(2020, 6, 20, 9, 0, 0), arrays.sim_len, 30.0)
+    tpp[35:] = summer                                   # half of the points run on a June morning
+    arrays.time_per_point = tpp
+    r, sg, sc, ref, _ = _run_both(rslib, oracle, arrays, settings, params)
+    assert rslib.last_batch_stats()["groups"] == 2 and np.array_equal(sg, sc)
+    _assert_parity(r, max_mismatch=0.1)
+    # the sun is up in June: the shadowing code really ran and changed the result
+    assert np.abs(arrays.out["TsurfOut"][35:, -1] - arrays.out["TsurfOut"][:35, -1]).max() > 1e-3
+
+
+def test_output_depth_force_tsurf_and_layer_count_variants(rslib, oracle):
+    # per-step depth array
+    arrays, settings, params, _ = synth.make_case(40, 3, seed=30, analysis_hours=2)
+    arrays.Depth[:, :] = 0.04
+    arrays.Depth[::3, 100:] = 0.0
+    arrays.Depth[1::3, :] = 5.0        # deeper than the last layer
+    _assert_parity(_run_both(rslib, oracle, arrays, settings, params)[0], max_mismatch=0.1)
+    # run-constant tsurfOutputDepth, forced surface temperature, NLayers != 15 (generic kernel)
+    for kw, nl in ((dict(tsurf_output_depth=0.06), 15), (dict(force_tsurf=1), 15),
+                   (dict(tsurf_output_depth=0.0), 12), ({}, 20), ({}, 4)):
+        arrays, settings, params, _ = synth.make_case(40, 3, seed=31, analysis_hours=2, nlayers=nl,
+                                                       settings_kw=kw)
+        r, sg, sc, _, _ = _run_both(rslib, oracle, arrays, settings, params)
+        _assert_parity(r, max_mismatch=0.1)
+        assert np.array_equal(sg, sc)
+        assert rslib.last_launch()["nlayers"] == nl
+
+
+def test_parameter_overrides_reach_the_kernel(rslib, oracle):
+    arrays, settings, _, _ = synth.make_case(64, 6, seed=32)
+    params = abi.default_parameters(30.0, Emiss=0.9, ZMom=0.2, AlbSnow=0.7, freezing_limit_normal=-0.5,
+                                    ice_melting_limit_normal=0.4, TClimG=4.0, Albedo_surroundings=0.3)
+    r, sg, sc, ref, _ = _run_both(rslib, oracle, arrays, settings, params)
+    _assert_parity(r, max_mismatch=0.1)
+    base = arrays.copy()
+    rslib.run_batch(base, settings, abi.default_parameters(30.0))
+    assert np.abs(base.out["TsurfOut"] - arrays.out["TsurfOut"]).max() > 1e-2
+
+
+def test_device_resident_coarse_forcing_and_strided_output(rslib, oracle):
+    """Coarse hourly records interpolated on the device (N1) + output every 120th step (N2) against
+    the oracle fed with host-interpolated full-resolution arrays."""
+    import torch
+    arrays, settings, params, rec = synth.make_case(200, 12, seed=33)
+    ref = arrays.copy()
+    st_cpu, _ = oracle.run_batch(ref, settings, params, nthreads=8)
+    rslib.set_model(settings, params)
+    for stride in (1, 120):
+        db = rslib.DeviceBatch(200, arrays.sim_len, n_records=rec.nrec, coarse=True, horizons=True,
+                               out_stride=stride)
+        db.load_records(rec)
+        db.time_fields.copy_(torch.from_numpy(arrays.time))
+        db.load_local(arrays.local, arrays.local_horizons)
+        db.out.fill_(7.0)
+        db.run()
+        torch.cuda.synchronize()
+        got = db.outputs()
+        want = {k: v[:, ::stride] for k, v in ref.out.items()}
+        _assert_parity(compare(got, want), max_mismatch=0.1)
+        assert np.array_equal(db.status.cpu().numpy()[:200], st_cpu)
+        cnt = db.counters.cpu().numpy()
+        assert cnt[rslib.CNT_EXECUTED_STEPS] == 200 * arrays.sim_len
+    assert got["TsurfOut"].shape == (200, 13)
+
+
+def test_device_resident_full_resolution_matches_batch_entry(rslib):
+    """Same inputs through the SoA device entry and through roadsurf_run_batch: bit-identical."""
+    import torch
+    arrays, settings, params, _ = synth.make_case(100, 3, seed=34, analysis_hours=2, use_coupling=1,
+                                                   use_relaxation=1, settings_kw=dict(coupling_minutes=60))
+    rslib.set_model(settings, params)
+    db = rslib.DeviceBatch(100, arrays.sim_len, horizons=True, coupling=True)
+    db.load_point_arrays(arrays)
+    db.run()
+    torch.cuda.synchronize()
+    got = db.outputs()
+    rslib.run_batch(arrays, settings, params)
+    for k in got:
+        assert np.array_equal(got[k], arrays.out[k]), k
+
+
+def test_point_order_does_not_matter(rslib):
+    """Indexing is bit-exact: permuting the points permutes the outputs and nothing else."""
+    arrays, settings, params, _ = synth.make_case(130, 4, seed=35, analysis_hours=4, use_coupling=1,
+                                                   use_relaxation=1)
+    perm = np.random.default_rng(1).permutation(130)
+    shuffled = abi.PointArrays(130, arrays.sim_len)
+    for n in abi.INPUT_DOUBLE_FIELDS:
+        getattr(shuffled, n[2:])[:] = getattr(arrays, n[2:])[perm]
+    shuffled.PrecPhase[:] = arrays.PrecPhase[perm]
+    shuffled.local_horizons[:] = arrays.local_horizons[perm]
+    shuffled.time[:] = arrays.time
+    for q, p in enumerate(perm):
+        shuffled.local[q] = arrays.local[int(p)]
+    rslib.run_batch(arrays, settings, params)
+    rslib.run_batch(shuffled, settings, params)
+    for k in arrays.out:
+        assert np.array_equal(shuffled.out[k], arrays.out[k][perm]), k
+
+
+def test_full_size_properties_c4_shard(rslib, oracle):
+    """BASELINE config 4 at one GPU's share (10^7 / 8 points, 24 h, hourly forcing, hourly output):
+    size-independent properties + sampled parity.  Replicated points must give identical results
+    wherever they sit in the grid; a random sample is checked against the oracle."""
+    import torch
+    base_n, P = 2048, 1_250_000
+    arrays, settings, params, rec = synth.make_case(base_n, 24, seed=36)
+    rslib.set_model(settings, params)
+    small = rslib.DeviceBatch(base_n, arrays.sim_len, n_records=rec.nrec, coarse=True, horizons=True,
+                              out_stride=120)
+    small.load_records(rec)
+    small.time_fields.copy_(torch.from_numpy(arrays.time))
+    small.load_local(arrays.local, arrays.local_horizons)
+    big = rslib.DeviceBatch(P, arrays.sim_len, n_records=rec.nrec, coarse=True, horizons=True, out_stride=120)
+    idx = torch.arange(big.ld, device="cuda") % base_n
+    big.forcing.copy_(small.forcing[:, :, idx])
+    big.record_step.copy_(small.record_step)
+    big.time_fields.copy_(small.time_fields)
+    big.local.copy_(small.local[:, idx])
+    big.local[rslib.L_ACTIVE, P:] = 0
+    big.horizons.copy_(small.horizons[:, idx])
+    big.run()
+    small.run()
+    torch.cuda.synchronize()
+    out_big, out_small = big.out[:, :, :P], small.out[:, :, :base_n]
+    assert torch.equal(out_big, out_small[:, :, idx[:P]])                 # replication invariance
+    assert int(big.counters[rslib.CNT_EXECUTED_STEPS]) == P * arrays.sim_len
+    assert int((big.status[:P] != 0).sum()) == 0 and int((big.status[P:] != rslib.ST_NOT_RUN).sum()) == 0
+    big.run()                                                             # idempotent re-run
+    torch.cuda.synchronize()
+    assert torch.equal(big.out[:, :, :P], out_small[:, :, idx[:P]])
+    # sampled parity against the oracle
+    sample = np.random.default_rng(2).choice(base_n, 128, replace=False)
+    sub = abi.PointArrays(128, arrays.sim_len)
+    for n in abi.INPUT_DOUBLE_FIELDS:
+        getattr(sub, n[2:])[:] = getattr(arrays, n[2:])[sample]
+    sub.PrecPhase[:] = arrays.PrecPhase[sample]
+    sub.local_horizons[:] = arrays.local_horizons[sample]
+    sub.time[:] = arrays.time
+    for q, p in enumerate(sample):
+        sub.local[q] = arrays.local[int(p)]
+    oracle.run_batch(sub, settings, params, nthreads=8)
+    got_all = small.outputs()
+    got = {k: v[sample] for k, v in got_all.items()}
+    want = {k: v[:, ::120] for k, v in sub.out.items()}
+    _assert_parity(compare(got, want), max_mismatch=0.1)

@@ -1,0 +1,148 @@
+"""Host-side logic that surrounds the kernel: forcing interpolation, read_input derivations,
+point sharding (world_size-2 gloo) and the synthetic generator."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+from roadsurf_b200 import abi, sharding, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _interpolate_like_json_source(raw, rawtime, simtime, miss=-100.0):
+    """Literal restatement of examples/example1/src/JsonSource.cpp:49-176 for one variable."""
+    out = np.full(len(simtime), -9999.9)
+    raw_pos = sim_pos = 0
+    if rawtime[0] < simtime[0]:
+        raw_pos = 0
+        while raw_pos < len(rawtime) and not rawtime[raw_pos] >= simtime[0]:
+            raw_pos += 1
+        raw_pos -= 1
+    elif simtime[0] < rawtime[0]:
+        while sim_pos < len(simtime) and not simtime[sim_pos] >= rawtime[0]:
+            sim_pos += 1
+    while raw_pos + 1 < len(rawtime) and sim_pos < len(simtime):
+        if abs(simtime[sim_pos] - rawtime[raw_pos]) < 0.01:
+            if raw[raw_pos] > miss:
+                out[sim_pos] = raw[raw_pos]
+            sim_pos += 1
+        elif abs(simtime[sim_pos] - rawtime[raw_pos + 1]) < 0.01:
+            raw_pos += 1
+        else:
+            if raw[raw_pos] > miss and raw[raw_pos + 1] > miss:
+                out[sim_pos] = raw[raw_pos] + (simtime[sim_pos] - rawtime[raw_pos]) * (
+                    raw[raw_pos + 1] - raw[raw_pos]) / (rawtime[raw_pos + 1] - rawtime[raw_pos])
+            sim_pos += 1
+    return out
+
+
+def test_interpolation_matches_json_source_semantics():
+    rec = synth.draw_records(3, 5, seed=9, start=synth.FORECAST_START)
+    rec.tair[1, 2] = -9999.9          # a missing record blanks both neighbouring intervals
+    sim_len = 1 + 3 * 120
+    fields = synth.interpolate_records(rec, sim_len)
+    rawtime = [int(s) * 30 for s in rec.record_step]
+    simtime = [i * 30 for i in range(sim_len)]
+    for p in range(3):
+        want = _interpolate_like_json_source(rec.tair[p], rawtime, simtime)
+        assert np.array_equal(fields["tair"][p], want)
+        want = _interpolate_like_json_source(rec.LW_net[p], rawtime, simtime, miss=-1000.0)
+        assert np.array_equal(fields["LW_net"][p], want)
+    # precipitation phase: the record itself at record times, otherwise the NEXT record
+    assert fields["PrecPhase"].dtype == np.int32
+    assert np.array_equal(fields["PrecPhase"][:, 0], rec.PrecPhase[:, 0].astype(np.int32))
+    assert np.array_equal(fields["PrecPhase"][:, 1], rec.PrecPhase[:, 1].astype(np.int32))
+    assert np.array_equal(fields["PrecPhase"][:, 120], rec.PrecPhase[:, 1].astype(np.int32))
+    assert (fields["tair"][1, 121:360] < -9000).all() and fields["tair"][1, 120] > -100
+
+
+def test_read_input_derivations_follow_the_example():
+    """examples/example1/src/roadrunner.cpp:157-278."""
+    arrays, settings, params, rec = synth.make_case(3, 6, seed=4, analysis_hours=6, use_coupling=1,
+                                                    use_relaxation=1)
+    for p in range(3):
+        lp = arrays.local[p]
+        assert lp.InitLenI == 721                       # GetLatestObsIndex: count of observed steps
+        assert lp.tair_relax == arrays.tair[p, 721]     # first pure-forecast value
+        assert lp.couplingIndexI == 720                 # 0-based index of the last observation...
+        assert (arrays.TSurfObs[p, 361:721] < -9000).all()   # ...blanked over the coupling window
+        assert arrays.TSurfObs[p, 360] > -100 and lp.couplingTsurf > -100
+    # without observations nothing is derived and the library disables both features per point
+    arrays, settings, params, rec = synth.make_case(2, 2, seed=4, use_coupling=1, use_relaxation=1)
+    assert arrays.local[0].couplingIndexI == -9999 and arrays.local[0].tair_relax < -9000
+
+
+def test_time_axis_and_case_shape():
+    arrays, settings, params, rec = synth.make_case(2, 24, seed=1)
+    assert settings.SimLen == arrays.sim_len == 2881        # 1 + 24 h * 120
+    t = arrays.time
+    assert tuple(t[:, 0]) == (2019, 12, 2, 0, 0, 0) and tuple(t[:, 1]) == (2019, 12, 2, 0, 0, 30)
+    assert tuple(t[:, -1]) == (2019, 12, 3, 0, 0, 0)
+    arrays, settings, params, rec = synth.make_case(2, 48, seed=1, analysis_hours=6)
+    assert settings.SimLen == 6481 and tuple(arrays.time[:, 0]) == (2019, 12, 1, 18, 0, 0)
+    assert (arrays.Rhz <= 100).all() and (arrays.SW >= 0).all() and (arrays.SW_dir <= arrays.SW + 1e-12).all()
+
+
+def test_point_arrays_pointers_address_rows():
+    arrays, settings, params, rec = synth.make_case(3, 2, seed=2)
+    ins = arrays.input_pointers()
+    for p in range(3):
+        assert ins[p].inputLen == arrays.sim_len
+        assert ins[p].c_tair[5] == arrays.tair[p, 5] and ins[p].c_PrecPhase[7] == arrays.PrecPhase[p, 7]
+        assert ins[p].c_hour[130] == 1 and ins[p].c_local_horizons[359] == arrays.local_horizons[p, 359]
+    outs = arrays.output_pointers()
+    outs[2].c_TsurfOut[3] = 1.25
+    assert arrays.out["TsurfOut"][2, 3] == 1.25
+    cp = arrays.copy()
+    cp.tair[0, 0] += 1.0
+    assert cp.tair[0, 0] != arrays.tair[0, 0] and cp.local[1].lat == arrays.local[1].lat
+
+
+def test_shard_ranges_partition_the_points():
+    for n in (0, 1, 7, 100000, 10**7, 51 * 10**6):
+        for w in (1, 2, 4, 8):
+            parts = [sharding.shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_gloo_reduction_and_sharding(tmp_path):
+    """The N>1 host path of bench.py on CPU: two gloo ranks shard the points, time their shard and
+    reduce max-over-ranks / sum-over-ranks."""
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, json
+        sys.path.insert(0, {ROOT!r})
+        import torch.distributed as dist
+        from roadsurf_b200 import sharding
+        dist.init_process_group("gloo")
+        r, w = dist.get_rank(), dist.get_world_size()
+        a, b = sharding.shard_range(1001, r, w)
+        sharding.barrier()
+        tmax = sharding.reduce_over_ranks(10.0 + r, "max")
+        total = sharding.reduce_over_ranks(b - a, "sum")
+        if r == 0:
+            print(json.dumps(dict(world=w, tmax=tmax, total=total, mine=[a, b])))
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    res = json.loads(line)
+    assert res == dict(world=2, tmax=11.0, total=1001.0, mine=[0, 500])
+
+
+def test_default_settings_and_copy_semantics():
+    s = abi.default_settings(100)
+    assert (s.DTSecs, s.NLayers, s.coupling_minutes, s.couplingEffectReduction, s.outputStep) == (
+        30.0, 15, 180, 14400.0, 60)
+    assert s.force_tsurf == 0 and s.tsurfOutputDepth < 0
