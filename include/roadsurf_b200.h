@@ -267,6 +267,8 @@ typedef struct RsDeviceBatch
   double* scratch;            /* [RS_SCRATCH_NPLANES(NLayers)][ld] work space; required when the
                                  model has use_coupling == 1, else may be NULL */
   unsigned long long* counters; /* optional [RS_CNT_N] device counters (accumulated), or NULL */
+  double* solar;              /* [sim_len][4] work space: per-step solar table (time-only part of
+                                 src/SunPosition.f90), filled by the library at every launch */
 } RsDeviceBatch;
 
 enum

@@ -5,7 +5,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libroadsurf_b200.so")
+LIB = os.path.join(HERE, os.environ.get("ROADSURF_B200_LIBNAME", "libroadsurf_b200.so"))
 SOURCES = ("rs_kernel.cu", "rs_host.cu", "rs_model.cpp")
 
 # -fmad=false: no FMA contraction, like a generic x86-64 gfortran build of the reference, so that
@@ -35,7 +35,7 @@ def build_library(force=False, verbose=False, extra_flags=()):
     """Compile every CUDA source of the package into roadsurf_b200/libroadsurf_b200.so."""
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags)
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + os.environ.get("ROADSURF_B200_NVCC_EXTRA", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]

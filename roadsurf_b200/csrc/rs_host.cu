@@ -231,6 +231,10 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
                            cudaMemcpyHostToDevice, stream));
       sh.stats.h2d_bytes += sizeof(int) * 6 * sim_len;
     }
+    DeviceMem d_solar;
+    CU(d_solar.alloc(sizeof(double) * 4 * sim_len));
+    CU(static_cast<cudaError_t>(rs_launch_solar(d_tf.as<int>(), sim_len, d_solar.as<double>(), stream)));
+    ++sh.stats.kernel_launches;
 
     for (size_t s0 = 0; s0 < slots.size(); s0 += max_slots)
     {
@@ -365,6 +369,7 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
       a.tf = d_tf.as<int>();
       a.local = d_local.as<double>();
       a.horizons = any_sky ? d_hor.as<double>() : nullptr;
+      a.solar = d_solar.as<double>();
       a.out = d_out.as<double>();
       a.status = d_status.as<int>();
       a.scratch = model.use_coupling ? d_scratch.as<double>() : nullptr;
@@ -536,10 +541,15 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
   d_rs = static_cast<int*>(tmp);
   CU(pool_get(sh.device, 102, sizeof(unsigned long long) * RS_CNT_N, &tmp));
   d_counters = static_cast<unsigned long long*>(tmp);
+  double* d_solar = nullptr;
+  CU(pool_get(sh.device, 103, sizeof(double) * 4 * b->sim_len, &tmp));
+  d_solar = static_cast<double*>(tmp);
   CU(cudaMemcpyAsync(d_tf, b->time_fields, sizeof(int) * 6 * b->sim_len, cudaMemcpyHostToDevice, streams[0]));
   if (b->forcing_mode == 1)
     CU(cudaMemcpyAsync(d_rs, b->record_step, sizeof(int) * b->n_records, cudaMemcpyHostToDevice, streams[0]));
   CU(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * RS_CNT_N, streams[0]));
+  CU(static_cast<cudaError_t>(rs_launch_solar(d_tf, b->sim_len, d_solar, streams[0])));
+  ++sh.stats.kernel_launches;
   CU(cudaStreamSynchronize(streams[0]));
   sh.stats.h2d_bytes += sizeof(int) * (6 * b->sim_len + b->n_records);
 
@@ -589,6 +599,7 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     a.tf = d_tf;
     a.local = d_local[s];
     a.horizons = d_hor[s];
+    a.solar = d_solar;
     a.out = d_out[s];
     a.status = d_status[s];
     a.scratch = d_scratch[s];
@@ -734,7 +745,7 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   if (b->sim_len < 1 || b->out_stride < 1 || b->n_out != (b->sim_len + b->out_stride - 1) / b->out_stride)
     return fail(RS_ERR_BAD_ARGUMENT, "bad sim_len / out_stride / n_out");
   if (b->nvar != RS_F_NVAR && b->nvar != RS_F_NVAR_DEPTH) return fail(RS_ERR_BAD_ARGUMENT, "nvar must be 11 or 12");
-  if (!b->forcing || !b->time_fields || !b->local || !b->out || !b->status)
+  if (!b->forcing || !b->time_fields || !b->local || !b->out || !b->status || !b->solar)
     return fail(RS_ERR_BAD_ARGUMENT, "null device pointer in batch");
   if (b->forcing_mode == 0)
   {
@@ -762,6 +773,7 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   a.tf = b->time_fields;
   a.local = b->local;
   a.horizons = b->horizons;
+  a.solar = b->solar;
   a.out = b->out;
   a.status = b->status;
   a.state = b->state;
@@ -769,6 +781,8 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   a.counters = b->counters;
   RsLaunchInfo li;
   std::memset(&li, 0, sizeof li);
+  CU(static_cast<cudaError_t>(rs_launch_solar(b->time_fields, b->sim_len, b->solar, stream)));
+  ++g_launches_total;
   CU(static_cast<cudaError_t>(rs_launch_run(&a, m.nlayers, stream, &li.grid, &li.block, &li.regs_per_thread)));
   li.nlayers = m.nlayers;
   li.forcing_mode = b->forcing_mode;

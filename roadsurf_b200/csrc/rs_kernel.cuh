@@ -18,6 +18,7 @@ struct RsArgs
   const int* tf;            // [6][sim_len]
   const double* local;      // [RS_L_NLOCAL][ld]
   const double* horizons;   // [360][ld] or null
+  const double* solar;      // [sim_len][4] per-step solar table (rs_launch_solar)
   double* out;              // [6][n_out][ld]
   int* status;
   double* state;
@@ -26,9 +27,14 @@ struct RsArgs
 };
 
 #define RS_BLOCK 128
+// Resident blocks per SM the step kernel is compiled for (register cap = 65536 / (128 * n)).
+#ifndef RS_MIN_BLOCKS
+#define RS_MIN_BLOCKS 3
+#endif
 
 // Host-callable launchers (rs_kernel.cu).  Return a cudaError_t as int.
 int rs_upload_model(const RsModel* m);
+int rs_launch_solar(const int* tf, int sim_len, double* table, void* stream);
 int rs_launch_run(const RsArgs* a, int nlayers, void* stream, int* grid, int* block, int* regs);
 int rs_launch_transpose_to_soa(const double* src, long long src_ld, int npoints, int n, double* dst,
                                int ld, void* stream);

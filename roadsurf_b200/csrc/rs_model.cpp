@@ -139,6 +139,16 @@ int rs_build_model(const InputSettings* s, const InputParameters* p, RsModel* m,
   }
   m->hs1_dz = m->ZDpth[2] - m->ZDpth[1];
   m->two_dt = 2.0 * s->DTSecs;
+  m->inv_two_dt = 1.0 / m->two_dt;
+  m->inv_DT = 1.0 / s->DTSecs;
+  m->inv_3600 = 1.0 / 3600.0;
+  m->inv_1000 = 1.0 / 1000.0;
+  m->inv_3364 = 1.0 / 3364.0;
+  m->inv_1p5 = 1.0 / 1.5;
+  m->inv_4h = 1.0 / static_cast<double>(4.f * 3600.f);
+  m->inv_CER = 1.0 / s->couplingEffectReduction;
+  m->WatMHeatDens = p->WatMHeat * p->WatDens;
+  m->inv_WatMHeatDens = 1.0 / m->WatMHeatDens;
 
   // fixed output depth, resolved once (getTempAtDepth with a run-constant depth)
   m->depth_mode = 0;

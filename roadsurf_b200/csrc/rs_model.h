@@ -50,6 +50,10 @@ struct RsModel
   double WCont[RS_MAX_LAYERS + 2];   // 1..N                          src/Initialization.f90:207-213
   double hs1_dz;                     // ZDpth(2)-ZDpth(1)             src/BalanceModel.f90:240-241
   double two_dt;                     // 2.0*DTSecs
+  // Correctly rounded reciprocals of run constants: x / c is evaluated as q = x*rc,
+  // q + fma(-q, c, x)*rc, which equals the IEEE quotient (see div_const in rs_kernel.cu).
+  double inv_two_dt, inv_DT, inv_3600, inv_1000, inv_3364, inv_1p5, inv_4h, inv_CER;
+  double WatMHeatDens, inv_WatMHeatDens;   // WatMHeat*WatDens and its reciprocal
   // fixed output depth (tsurfOutputDepth >= 0): 0 = mean of layers 1,2; 1 = Tmp(1);
   // 2 = Tmp(N+1); 3 = interpolate between depth_idx and depth_idx+1   src/BalanceModel.f90:390-417
   int depth_mode;

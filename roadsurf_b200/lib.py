@@ -12,7 +12,7 @@ import numpy as np
 from . import abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libroadsurf_b200.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("ROADSURF_B200_LIBNAME", "libroadsurf_b200.so"))
 
 # enums of include/roadsurf_b200.h
 ST_FAILED, ST_BAD_INPUT, ST_ABNORMAL_TSURF, ST_COUPLING_USED, ST_COUPLING_FAILED = 1, 2, 4, 8, 16
@@ -60,7 +60,8 @@ class RsDeviceBatch(C.Structure):
                 ("forcing", C.c_void_p), ("record_step", C.c_void_p), ("time_fields", C.c_void_p),
                 ("local", C.c_void_p), ("horizons", C.c_void_p), ("out", C.c_void_p),
                 ("out_stride", C.c_int), ("n_out", C.c_int), ("status", C.c_void_p),
-                ("state", C.c_void_p), ("scratch", C.c_void_p), ("counters", C.c_void_p)]
+                ("state", C.c_void_p), ("scratch", C.c_void_p), ("counters", C.c_void_p),
+                ("solar", C.c_void_p)]
 
 
 class RsHostBatch(C.Structure):
@@ -213,6 +214,7 @@ class DeviceBatch:
         self.state = torch.zeros((state_nplanes(nlayers), self.ld), **f64) if state else None
         self.scratch = torch.zeros((scratch_nplanes(nlayers), self.ld), **f64) if coupling else None
         self.counters = torch.zeros(CNT_N, dtype=torch.int64, device=device)
+        self.solar = torch.zeros((self.sim_len, 4), **f64)
 
     def descriptor(self):
         def ptr(t):
@@ -223,7 +225,7 @@ class DeviceBatch:
                              time_fields=ptr(self.time_fields), local=ptr(self.local),
                              horizons=ptr(self.horizons), out=ptr(self.out), out_stride=self.out_stride,
                              n_out=self.n_out, status=ptr(self.status), state=ptr(self.state),
-                             scratch=ptr(self.scratch), counters=ptr(self.counters))
+                             scratch=ptr(self.scratch), counters=ptr(self.counters), solar=ptr(self.solar))
 
     def run(self, stream=None):
         """Asynchronous launch on `stream` (a torch.cuda.Stream; default: the current stream)."""

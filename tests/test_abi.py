@@ -29,6 +29,7 @@ int main(void) {
   O(LocalParameters, sky_view); O(LocalParameters, InitLenI);
   S(RsDeviceBatch); S(RsBatchStats); S(RsLaunchInfo);
   O(RsDeviceBatch, forcing); O(RsDeviceBatch, out_stride); O(RsDeviceBatch, scratch); O(RsDeviceBatch, counters);
+  O(RsDeviceBatch, solar);
   return 0;
 }
 """
