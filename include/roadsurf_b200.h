@@ -338,6 +338,12 @@ int roadsurf_fill(double* dst, int64_t n, double value, void* stream);
  * register-resident DFMA kernel; used as the fp64 roofline denominator by bench.py. */
 double roadsurf_measure_fp64_tflops(int iterations);
 
+/* Arithmetic self-test on the current device: the kernel's branch-free reciprocal, division and
+ * constant-division primitives against the compiler's IEEE division on `n` random operand pairs.
+ * mismatches[0..2] receive the number of results that differ (must all be 0); returns the number
+ * of pairs tested, or -1 on error. */
+long long roadsurf_selftest_arith(long long n, unsigned long long seed, long long* mismatches);
+
 /* Name of the most recently launched step kernel variant and its launch geometry. */
 typedef struct RsLaunchInfo
 {

@@ -824,6 +824,16 @@ double roadsurf_measure_fp64_tflops(int iterations)
   return rs_measure_fp64(iterations > 0 ? iterations : 20000);
 }
 
+long long roadsurf_selftest_arith(long long n, unsigned long long seed, long long* mismatches)
+{
+  if (roadsurf_device_count() < 1)
+  {
+    fail(RS_ERR_NO_DEVICE, "no CUDA device visible");
+    return -1;
+  }
+  return rs_selftest_arith(n, seed, mismatches);
+}
+
 void roadsurf_last_launch(RsLaunchInfo* info)
 {
   if (info)

@@ -46,3 +46,4 @@ int rs_launch_pack_forcing(const double* stage, int npoints_chunk, int p0, int s
 int rs_launch_unpack_out(const double* out, int ld, int n_out, int p0, int npoints_chunk,
                          double* stage, void* stream);
 double rs_measure_fp64(int iterations);
+long long rs_selftest_arith(long long n, unsigned long long seed, long long* bad3);

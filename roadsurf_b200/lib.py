@@ -30,7 +30,8 @@ EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roa
            "roadsurf_run_host_soa",
            "roadsurf_last_batch_stats", "roadsurf_set_model", "roadsurf_run_device",
            "roadsurf_transpose_to_soa", "roadsurf_transpose_from_soa", "roadsurf_fill",
-           "roadsurf_measure_fp64_tflops", "roadsurf_last_launch", "roadsurf_version")
+           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_last_launch",
+           "roadsurf_version")
 
 
 def state_nplanes(nlayers):
@@ -115,6 +116,8 @@ def load():
     lib.roadsurf_fill.restype = C.c_int
     lib.roadsurf_measure_fp64_tflops.argtypes = [C.c_int]
     lib.roadsurf_measure_fp64_tflops.restype = C.c_double
+    lib.roadsurf_selftest_arith.argtypes = [C.c_longlong, C.c_ulonglong, P(C.c_longlong)]
+    lib.roadsurf_selftest_arith.restype = C.c_longlong
     lib.roadsurf_last_launch.argtypes = [P(RsLaunchInfo)]
     _lib = lib
     return lib
@@ -291,3 +294,12 @@ def measure_fp64_tflops(iterations=20000):
     if v < 0:
         raise RoadSurfError(load().roadsurf_last_error().decode())
     return v
+
+
+def selftest_arith(n=200_000_000, seed=12345):
+    """(pairs tested, [rcp, div, div_const] mismatch counts) of the arithmetic self-test."""
+    bad = (C.c_longlong * 3)()
+    tested = load().roadsurf_selftest_arith(int(n), int(seed), bad)
+    if tested < 0:
+        raise RoadSurfError(load().roadsurf_last_error().decode())
+    return int(tested), [int(b) for b in bad]

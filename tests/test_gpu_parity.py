@@ -299,3 +299,10 @@ def test_full_size_properties_c4_shard(rslib, oracle):
     got = {k: v[sample] for k, v in got_all.items()}
     want = {k: v[:, ::120] for k, v in sub.out.items()}
     _assert_parity(compare(got, want), max_mismatch=0.1)
+
+
+def test_branch_free_division_primitives_are_ieee_exact(rslib):
+    """The kernel replaces `a / b` by a reciprocal seed + Newton + remainder correction without the
+    compiler's exponent-range test: every result must equal the IEEE quotient bit for bit."""
+    tested, bad = rslib.selftest_arith(400_000_000, seed=2024)
+    assert tested >= 400_000_000 and bad == [0, 0, 0], (tested, bad)
