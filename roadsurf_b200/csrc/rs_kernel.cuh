@@ -26,12 +26,6 @@ struct RsArgs
   unsigned long long* counters;
 };
 
-#define RS_BLOCK 128
-// Resident blocks per SM the step kernel is compiled for (register cap = 65536 / (128 * n)).
-#ifndef RS_MIN_BLOCKS
-#define RS_MIN_BLOCKS 3
-#endif
-
 // Host-callable launchers (rs_kernel.cu).  Return a cudaError_t as int.
 int rs_upload_model(const RsModel* m);
 int rs_launch_solar(const int* tf, int sim_len, double* table, void* stream);
