@@ -338,6 +338,12 @@ int roadsurf_fill(double* dst, int64_t n, double value, void* stream);
  * register-resident DFMA kernel; used as the fp64 roofline denominator by bench.py. */
 double roadsurf_measure_fp64_tflops(int iterations);
 
+/* Run-time options.  "forcing_staging": 1 = in full-resolution mode stage the forcing of every warp
+ * through a ring of shared-memory tiles filled by TMA bulk copies a few steps ahead, 0 = direct
+ * coalesced read-only loads (default; measured 3-6 % faster on B200).  The default can
+ * also be set with the environment variable ROADSURF_B200_FORCING_STAGING=1.  Results are identical. */
+int roadsurf_set_option(const char* name, int value);
+
 /* Arithmetic self-test on the current device: the kernel's branch-free reciprocal, division and
  * constant-division primitives against the compiler's IEEE division on `n` random operand pairs.
  * mismatches[0..2] receive the number of results that differ (must all be 0); returns the number

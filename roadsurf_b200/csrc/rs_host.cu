@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -27,6 +28,19 @@ thread_local RsLaunchInfo g_launch;
 std::mutex g_model_mu;
 std::map<int, RsModel> g_models;  // device -> model currently in its constant memory
 int g_launches_total = 0;
+
+// Run-time options (roadsurf_set_option).  forcing_staging: 1 = full-resolution forcing through the
+// per-warp TMA ring in shared memory, 0 = direct read-only loads (default: measured faster).
+int g_opt_staging = -1;
+int opt_staging()
+{
+  if (g_opt_staging < 0)
+  {
+    const char* e = std::getenv("ROADSURF_B200_FORCING_STAGING");
+    g_opt_staging = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_opt_staging;
+}
 
 int fail(int code, const std::string& msg)
 {
@@ -376,7 +390,8 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
       a.counters = d_counters.as<unsigned long long>();
       CU(cudaEventRecord(ev0, stream));
       CU(static_cast<cudaError_t>(
-          rs_launch_run(&a, nl, stream, &sh.launch.grid, &sh.launch.block, &sh.launch.regs_per_thread)));
+          rs_launch_run(&a, nl, opt_staging(), stream, &sh.launch.grid, &sh.launch.block,
+                        &sh.launch.regs_per_thread, &sh.launch.smem_bytes)));
       CU(cudaEventRecord(ev1, stream));
       ++sh.stats.kernel_launches;
       sh.launch.nlayers = nl;
@@ -605,7 +620,8 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     a.scratch = d_scratch[s];
     a.counters = d_counters;
     CU(static_cast<cudaError_t>(
-        rs_launch_run(&a, nl, st, &sh.launch.grid, &sh.launch.block, &sh.launch.regs_per_thread)));
+        rs_launch_run(&a, nl, opt_staging(), st, &sh.launch.grid, &sh.launch.block, &sh.launch.regs_per_thread,
+                      &sh.launch.smem_bytes)));
     ++sh.stats.kernel_launches;
     sh.launch.nlayers = nl;
     sh.launch.forcing_mode = b->forcing_mode;
@@ -783,7 +799,8 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   std::memset(&li, 0, sizeof li);
   CU(static_cast<cudaError_t>(rs_launch_solar(b->time_fields, b->sim_len, b->solar, stream)));
   ++g_launches_total;
-  CU(static_cast<cudaError_t>(rs_launch_run(&a, m.nlayers, stream, &li.grid, &li.block, &li.regs_per_thread)));
+  CU(static_cast<cudaError_t>(rs_launch_run(&a, m.nlayers, opt_staging(), stream, &li.grid, &li.block,
+                                            &li.regs_per_thread, &li.smem_bytes)));
   li.nlayers = m.nlayers;
   li.forcing_mode = b->forcing_mode;
   li.launches_total = ++g_launches_total;
@@ -822,6 +839,16 @@ double roadsurf_measure_fp64_tflops(int iterations)
     return -1.0;
   }
   return rs_measure_fp64(iterations > 0 ? iterations : 20000);
+}
+
+int roadsurf_set_option(const char* name, int value)
+{
+  if (name && std::strcmp(name, "forcing_staging") == 0)
+  {
+    g_opt_staging = value ? 1 : 0;
+    return RS_OK;
+  }
+  return fail(RS_ERR_BAD_ARGUMENT, "unknown option");
 }
 
 long long roadsurf_selftest_arith(long long n, unsigned long long seed, long long* mismatches)

@@ -29,7 +29,8 @@ struct RsArgs
 // Host-callable launchers (rs_kernel.cu).  Return a cudaError_t as int.
 int rs_upload_model(const RsModel* m);
 int rs_launch_solar(const int* tf, int sim_len, double* table, void* stream);
-int rs_launch_run(const RsArgs* a, int nlayers, void* stream, int* grid, int* block, int* regs);
+int rs_launch_run(const RsArgs* a, int nlayers, int staged, void* stream, int* grid, int* block, int* regs,
+                  int* smem);
 int rs_launch_transpose_to_soa(const double* src, long long src_ld, int npoints, int n, double* dst,
                                int ld, void* stream);
 int rs_launch_transpose_from_soa(const double* src, int ld, int npoints, int n, double* dst,

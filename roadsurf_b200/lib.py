@@ -30,7 +30,7 @@ EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roa
            "roadsurf_run_host_soa",
            "roadsurf_last_batch_stats", "roadsurf_set_model", "roadsurf_run_device",
            "roadsurf_transpose_to_soa", "roadsurf_transpose_from_soa", "roadsurf_fill",
-           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_last_launch",
+           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_set_option", "roadsurf_last_launch",
            "roadsurf_version")
 
 
@@ -116,6 +116,8 @@ def load():
     lib.roadsurf_fill.restype = C.c_int
     lib.roadsurf_measure_fp64_tflops.argtypes = [C.c_int]
     lib.roadsurf_measure_fp64_tflops.restype = C.c_double
+    lib.roadsurf_set_option.argtypes = [C.c_char_p, C.c_int]
+    lib.roadsurf_set_option.restype = C.c_int
     lib.roadsurf_selftest_arith.argtypes = [C.c_longlong, C.c_ulonglong, P(C.c_longlong)]
     lib.roadsurf_selftest_arith.restype = C.c_longlong
     lib.roadsurf_last_launch.argtypes = [P(RsLaunchInfo)]
@@ -303,3 +305,7 @@ def selftest_arith(n=200_000_000, seed=12345):
     if tested < 0:
         raise RoadSurfError(load().roadsurf_last_error().decode())
     return int(tested), [int(b) for b in bad]
+
+
+def set_option(name, value):
+    _check(load().roadsurf_set_option(name.encode(), int(value)))

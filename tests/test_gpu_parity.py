@@ -306,3 +306,26 @@ def test_branch_free_division_primitives_are_ieee_exact(rslib):
     compiler's exponent-range test: every result must equal the IEEE quotient bit for bit."""
     tested, bad = rslib.selftest_arith(400_000_000, seed=2024)
     assert tested >= 400_000_000 and bad == [0, 0, 0], (tested, bad)
+
+
+def test_tma_staged_forcing_ring_gives_identical_results(rslib):
+    """Full-resolution forcing through the per-warp TMA/mbarrier ring in shared memory (option
+    "forcing_staging") against the default direct loads: bit-identical, including coupling rewinds
+    that restart the ring, per-step depth (12 planes) and the generic layer-count kernel."""
+    cases = [dict(analysis_hours=4, use_coupling=1, use_relaxation=1), dict(), dict(nlayers=9)]
+    for kw in cases:
+        arrays, settings, params, _ = synth.make_case(200, 6, seed=41, **kw)
+        if not kw:
+            arrays.Depth[:, 50:] = 0.05
+        staged = arrays.copy()
+        try:
+            rslib.set_option("forcing_staging", 1)
+            st1 = rslib.run_batch(staged, settings, params)
+            assert rslib.last_launch()["smem_bytes"] > 0
+        finally:
+            rslib.set_option("forcing_staging", 0)
+        st0 = rslib.run_batch(arrays, settings, params)
+        assert rslib.last_launch()["smem_bytes"] == 0
+        assert np.array_equal(st0, st1)
+        for k in arrays.out:
+            assert np.array_equal(arrays.out[k], staged.out[k]), (kw, k)
