@@ -188,6 +188,8 @@ typedef struct RsBatchStats
   int64_t executed_steps; /* point-steps actually executed, including coupling re-runs */
   int kernel_launches;
   int groups;            /* (time axis, coupling window) groups the batch was split into */
+  double wall_ms;        /* host wall-clock time spent inside the call */
+  double setup_ms;       /* of which: grouping, depth scan, device/pinned allocations */
 } RsBatchStats;
 void roadsurf_last_batch_stats(RsBatchStats* stats);
 

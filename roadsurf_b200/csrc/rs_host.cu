@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -79,35 +80,36 @@ int set_model_on_current_device(const InputSettings* settings, const InputParame
   return RS_OK;
 }
 
-struct DeviceMem
+// Run fn(k) for k in [0, n) on up to `nthreads` host threads (the caller's thread included).
+void parallel_for(int n, int nthreads, const std::function<void(int)>& fn)
 {
-  void* p = nullptr;
-  ~DeviceMem()
+  if (n <= 0) return;
+  nthreads = std::max(1, std::min(nthreads, n));
+  if (nthreads == 1)
   {
-    if (p) cudaFree(p);
+    for (int k = 0; k < n; ++k) fn(k);
+    return;
   }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
-  template <class T>
-  T* as() const
-  {
-    return static_cast<T*>(p);
-  }
-};
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (;;)
+    {
+      const int k = next.fetch_add(1);
+      if (k >= n) break;
+      fn(k);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+}
 
-struct PinnedMem
+int host_threads()
 {
-  void* p = nullptr;
-  ~PinnedMem()
-  {
-    if (p) cudaFreeHost(p);
-  }
-  cudaError_t alloc(size_t bytes) { return cudaMallocHost(&p, bytes ? bytes : 8); }
-  template <class T>
-  T* as() const
-  {
-    return static_cast<T*>(p);
-  }
-};
+  const unsigned hc = std::thread::hardware_concurrency();
+  return static_cast<int>(std::max(1u, std::min(hc ? hc : 4u, 32u)));
+}
 
 // What the kernel will decide about a point's coupling window (src/InputOutput.f90:34-36,
 // src/Coupling.f90:510-519): used only to order slots so that every warp has one window.
@@ -126,11 +128,86 @@ struct Shard
   RsLaunchInfo launch{};
 };
 
+// Grow-only device and pinned-host work space, one buffer per (device, slot), reused across calls so
+// that a steady-state call does no cudaMalloc / cudaMallocHost (both cost tens to hundreds of ms at
+// these sizes).
+struct PoolEntry
+{
+  void* p = nullptr;
+  size_t cap = 0;
+};
+std::mutex g_pool_mu;
+std::map<std::pair<int, int>, PoolEntry> g_pool;
+
+cudaError_t pool_get(int device, int slot, size_t bytes, void** out)
+{
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  PoolEntry& e = g_pool[{device, slot}];
+  if (e.cap < bytes)
+  {
+    if (e.p) cudaFree(e.p);
+    e.p = nullptr;
+    e.cap = 0;
+    cudaError_t rc = cudaMalloc(&e.p, bytes);
+    if (rc != cudaSuccess) return rc;
+    e.cap = bytes;
+  }
+  *out = e.p;
+  return cudaSuccess;
+}
+
+std::map<std::pair<int, int>, PoolEntry> g_pinned_pool;
+
+// The pooled buffers of a device are used by one call at a time: concurrent callers (the reference
+// calls runsimulation from N host threads) are serialised per device, as the GPU would do anyway.
+std::mutex g_device_mu[64];
+
+cudaError_t pinned_get(int device, int slot, size_t bytes, void** out)
+{
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  PoolEntry& e = g_pinned_pool[{device, slot}];
+  if (e.cap < bytes)
+  {
+    if (e.p) cudaFreeHost(e.p);
+    e.p = nullptr;
+    e.cap = 0;
+    cudaError_t rc = cudaMallocHost(&e.p, bytes);
+    if (rc != cudaSuccess) return rc;
+    e.cap = bytes;
+  }
+  *out = e.p;
+  return cudaSuccess;
+}
+
+// Non-owning views with the DeviceMem / PinnedMem interface, backed by the pools above.
+struct PooledDevice
+{
+  void* p = nullptr;
+  cudaError_t alloc(int device, int slot, size_t bytes) { return pool_get(device, slot, bytes ? bytes : 8, &p); }
+  template <class T>
+  T* as() const
+  {
+    return static_cast<T*>(p);
+  }
+};
+struct PooledPinned
+{
+  void* p = nullptr;
+  cudaError_t alloc(int device, int slot, size_t bytes) { return pinned_get(device, slot, bytes ? bytes : 8, &p); }
+  template <class T>
+  T* as() const
+  {
+    return static_cast<T*>(p);
+  }
+};
+
 // Run points [first, first+count) of the batch on `device`.
 int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const* in,
               const InputSettings* settings, const InputParameters* params,
               const LocalParameters* const* local, int* status)
 {
+  std::lock_guard<std::mutex> device_lock(g_device_mu[sh.device & 63]);
+  const double setup0 = now_ms();
   CU(cudaSetDevice(sh.device));
   RsModel model;
   {
@@ -207,22 +284,23 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
     while (slots.size() % 32 != 0) slots.push_back(-1);
     ++sh.stats.groups;
 
-    bool any_depth = false, any_sky = false;
-    for (int p : g.points)
-    {
+    std::atomic<bool> any_depth_a(false), any_sky_a(false);
+    parallel_for(static_cast<int>(g.points.size()), host_threads(), [&](int k) {
+      const int p = g.points[k];
       const LocalParameters& lp = *local[p];
-      if (lp.sky_view < 1.0 && lp.sky_view > -0.01f) any_sky = true;
-      if (!any_depth)  // depth(1) and depth(SimLen) are read even when tsurfOutputDepth is set
+      if (lp.sky_view < 1.0 && lp.sky_view > -0.01f) any_sky_a = true;
+      if (!any_depth_a.load(std::memory_order_relaxed))  // depth(1), depth(SimLen) are read even with tsurfOutputDepth
       {
         const double* d = in[p]->c_Depth;
         for (int t = 0; t < sim_len; ++t)
           if (d[t] >= 0.0)
           {
-            any_depth = true;
+            any_depth_a = true;
             break;
           }
       }
-    }
+    });
+    const bool any_depth = any_depth_a, any_sky = any_sky_a;
     const int nvar = any_depth ? RS_F_NVAR_DEPTH : RS_F_NVAR;
 
     // ---- device batches that fit the memory budget -------------------------------------------
@@ -235,8 +313,8 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
     const size_t stage_budget = 192ull << 20;
     int chunk = static_cast<int>(std::max<size_t>(32, stage_budget / (sizeof(double) * sim_len * nvar) / 32 * 32));
 
-    DeviceMem d_tf;
-    CU(d_tf.alloc(sizeof(int) * 6 * sim_len));
+    PooledDevice d_tf;
+    CU(d_tf.alloc(sh.device, 209, sizeof(int) * 6 * sim_len));
     {
       const int* src[6] = {g.rep->c_year, g.rep->c_month, g.rep->c_day, g.rep->c_hour, g.rep->c_minute,
                            g.rep->c_second};
@@ -245,8 +323,8 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
                            cudaMemcpyHostToDevice, stream));
       sh.stats.h2d_bytes += sizeof(int) * 6 * sim_len;
     }
-    DeviceMem d_solar;
-    CU(d_solar.alloc(sizeof(double) * 4 * sim_len));
+    PooledDevice d_solar;
+    CU(d_solar.alloc(sh.device, 210, sizeof(double) * 4 * sim_len));
     CU(static_cast<cudaError_t>(rs_launch_solar(d_tf.as<int>(), sim_len, d_solar.as<double>(), stream)));
     ++sh.stats.kernel_launches;
 
@@ -254,21 +332,39 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
     {
       const int ld = static_cast<int>(std::min(max_slots, slots.size() - s0));
       chunk = std::min(chunk, ld);
-      DeviceMem d_forcing, d_out, d_local, d_hor, d_status, d_scratch, d_stage, d_counters;
-      CU(d_forcing.alloc(sizeof(double) * sim_len * nvar * ld));
-      CU(d_out.alloc(sizeof(double) * RS_O_NVAR * sim_len * ld));
-      CU(d_local.alloc(sizeof(double) * RS_L_NLOCAL * ld));
-      if (any_sky) CU(d_hor.alloc(sizeof(double) * 360 * ld));
-      CU(d_status.alloc(sizeof(int) * ld));
-      if (model.use_coupling) CU(d_scratch.alloc(sizeof(double) * RS_SCRATCH_NPLANES(nl) * ld));
-      CU(d_stage.alloc(sizeof(double) * static_cast<size_t>(chunk) * sim_len * std::max(nvar, (int)RS_O_NVAR)));
-      CU(d_counters.alloc(sizeof(unsigned long long) * RS_CNT_N));
+      PooledDevice d_forcing, d_out, d_local, d_hor, d_status, d_scratch, d_stage, d_stage2, d_counters;
+      const int dv = sh.device;
+      CU(d_forcing.alloc(dv, 200, sizeof(double) * sim_len * nvar * ld));
+      CU(d_out.alloc(dv, 201, sizeof(double) * RS_O_NVAR * sim_len * ld));
+      CU(d_local.alloc(dv, 202, sizeof(double) * RS_L_NLOCAL * ld));
+      if (any_sky) CU(d_hor.alloc(dv, 203, sizeof(double) * 360 * ld));
+      CU(d_status.alloc(dv, 204, sizeof(int) * ld));
+      if (model.use_coupling) CU(d_scratch.alloc(dv, 205, sizeof(double) * RS_SCRATCH_NPLANES(nl) * ld));
+      const size_t stage_bytes = sizeof(double) * static_cast<size_t>(chunk) * sim_len * std::max(nvar, (int)RS_O_NVAR);
+      CU(d_stage.alloc(dv, 206, stage_bytes));
+      CU(d_stage2.alloc(dv, 207, stage_bytes));
+      CU(d_counters.alloc(dv, 208, sizeof(unsigned long long) * RS_CNT_N));
       CU(cudaMemsetAsync(d_counters.p, 0, sizeof(unsigned long long) * RS_CNT_N, stream));
-      PinnedMem h_stage, h_local, h_hor, h_status;
-      CU(h_stage.alloc(sizeof(double) * static_cast<size_t>(chunk) * sim_len * std::max(nvar, (int)RS_O_NVAR)));
-      CU(h_local.alloc(sizeof(double) * RS_L_NLOCAL * ld));
-      if (any_sky) CU(h_hor.alloc(sizeof(double) * 360 * ld));
-      CU(h_status.alloc(sizeof(int) * ld));
+      PooledPinned h_stage, h_stage2, h_local, h_hor, h_status;
+      CU(h_stage.alloc(dv, 0, stage_bytes));
+      CU(h_stage2.alloc(dv, 1, stage_bytes));
+      double* h_st[2] = {h_stage.as<double>(), h_stage2.as<double>()};
+      double* d_st[2] = {d_stage.as<double>(), d_stage2.as<double>()};
+      const int nthreads = host_threads();
+      cudaEvent_t ev_free[2];  // staging buffer b may be reused once ev_free[b] has completed
+      for (int b = 0; b < 2; ++b) CU(cudaEventCreateWithFlags(&ev_free[b], cudaEventDisableTiming));
+      struct FreeGuard
+      {
+        cudaEvent_t* e;
+        ~FreeGuard()
+        {
+          cudaEventDestroy(e[0]);
+          cudaEventDestroy(e[1]);
+        }
+      } fguard{ev_free};
+      CU(h_local.alloc(dv, 2, sizeof(double) * RS_L_NLOCAL * ld));
+      if (any_sky) CU(h_hor.alloc(dv, 3, sizeof(double) * 360 * ld));
+      CU(h_status.alloc(dv, 4, sizeof(int) * ld));
 
       cudaEvent_t ev0, ev1;
       CU(cudaEventCreate(&ev0));
@@ -283,6 +379,7 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
         }
       } eguard{ev0, ev1};
 
+      sh.stats.setup_ms += now_ms() - setup0 - sh.stats.setup_ms - sh.stats.pack_ms;  // everything so far but packing
       // ---- per-point statics
       double t0 = now_ms();
       {
@@ -324,48 +421,57 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
         sh.stats.h2d_bytes += sizeof(double) * 360 * ld;
       }
 
-      // ---- forcing: caller's per-point arrays -> pinned [var][point][time] -> device -> SoA
-      for (int q0 = 0; q0 < ld; q0 += chunk)
+      // ---- forcing: caller's per-point arrays -> pinned [var][point][time] -> device -> SoA.
+      // Rows are packed by all host threads into one of two pinned buffers while the previous
+      // buffer is in flight (H2D copy + device-side transpose into the SoA tensor).
       {
-        const int npc = std::min(chunk, ld - q0);
-        t0 = now_ms();
-        double* S = h_stage.as<double>();
-        for (int q = 0; q < npc; ++q)
-        {
-          const int p = slots[s0 + q0 + q];
-          const size_t row = static_cast<size_t>(q) * sim_len;
-          const size_t plane = static_cast<size_t>(npc) * sim_len;
-          if (p < 0)
-          {
-            for (int v = 0; v < nvar; ++v) std::memset(S + v * plane + row, 0, sizeof(double) * sim_len);
-            continue;
-          }
-          const InputPointers* ip = in[p];
-          const double* src[RS_F_NVAR_DEPTH] = {ip->c_tair, ip->c_tdew, ip->c_VZ,     ip->c_Rhz,
-                                                ip->c_prec, ip->c_SW,   ip->c_LW,     ip->c_SW_dir,
-                                                ip->c_LW_net, ip->c_TSurfObs, nullptr, ip->c_Depth};
-          for (int v = 0; v < nvar; ++v)
-          {
-            double* dst = S + v * plane + row;
-            if (v == RS_F_PHASE)
-              for (int t = 0; t < sim_len; ++t) dst[t] = static_cast<double>(ip->c_PrecPhase[t]);
-            else
-              std::memcpy(dst, src[v], sizeof(double) * sim_len);
-          }
-        }
-        sh.stats.pack_ms += now_ms() - t0;
-        const size_t bytes = sizeof(double) * static_cast<size_t>(npc) * sim_len * nvar;
+        const double w0 = now_ms();
         CU(cudaEventRecord(ev0, stream));
-        CU(cudaMemcpyAsync(d_stage.p, h_stage.p, bytes, cudaMemcpyHostToDevice, stream));
+        int cidx = 0;
+        for (int q0 = 0; q0 < ld; q0 += chunk, ++cidx)
+        {
+          const int npc = std::min(chunk, ld - q0);
+          const int bsel = cidx & 1;
+          if (cidx >= 2) CU(cudaEventSynchronize(ev_free[bsel]));
+          t0 = now_ms();
+          double* S = h_st[bsel];
+          const size_t plane = static_cast<size_t>(npc) * sim_len;
+          parallel_for(npc, nthreads, [&](int q) {
+            const int p = slots[s0 + q0 + q];
+            const size_t row = static_cast<size_t>(q) * sim_len;
+            if (p < 0)
+            {
+              for (int v = 0; v < nvar; ++v) std::memset(S + v * plane + row, 0, sizeof(double) * sim_len);
+              return;
+            }
+            const InputPointers* ip = in[p];
+            const double* src[RS_F_NVAR_DEPTH] = {ip->c_tair, ip->c_tdew, ip->c_VZ,     ip->c_Rhz,
+                                                  ip->c_prec, ip->c_SW,   ip->c_LW,     ip->c_SW_dir,
+                                                  ip->c_LW_net, ip->c_TSurfObs, nullptr, ip->c_Depth};
+            for (int v = 0; v < nvar; ++v)
+            {
+              double* dst = S + v * plane + row;
+              if (v == RS_F_PHASE)
+                for (int t = 0; t < sim_len; ++t) dst[t] = static_cast<double>(ip->c_PrecPhase[t]);
+              else
+                std::memcpy(dst, src[v], sizeof(double) * sim_len);
+            }
+          });
+          sh.stats.pack_ms += now_ms() - t0;
+          const size_t bytes = sizeof(double) * plane * nvar;
+          CU(cudaMemcpyAsync(d_st[bsel], S, bytes, cudaMemcpyHostToDevice, stream));
+          CU(static_cast<cudaError_t>(
+              rs_launch_pack_forcing(d_st[bsel], npc, q0, sim_len, nvar, d_forcing.as<double>(), ld, stream)));
+          CU(cudaEventRecord(ev_free[bsel], stream));
+          ++sh.stats.kernel_launches;
+          sh.stats.h2d_bytes += bytes;
+        }
         CU(cudaEventRecord(ev1, stream));
-        CU(static_cast<cudaError_t>(rs_launch_pack_forcing(d_stage.as<double>(), npc, q0, sim_len, nvar,
-                                                           d_forcing.as<double>(), ld, stream)));
-        ++sh.stats.kernel_launches;
-        CU(cudaStreamSynchronize(stream));  // the pinned staging buffer is reused by the next chunk
+        CU(cudaStreamSynchronize(stream));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev0, ev1);
-        sh.stats.h2d_ms += ms;
-        sh.stats.h2d_bytes += bytes;
+        sh.stats.h2d_ms += ms;  // device-side time of the input phase (copies + transposes, overlapped with packing)
+        (void)w0;
       }
 
       // ---- the step kernel
@@ -403,36 +509,56 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
         sh.stats.kernel_ms += ms;
       }
 
-      // ---- outputs: SoA -> [var][point][time] -> pinned -> caller's arrays
-      for (int q0 = 0; q0 < ld; q0 += chunk)
+      // ---- outputs: SoA -> [var][point][time] -> pinned -> caller's arrays, double buffered: the
+      // host threads scatter chunk c-1 into the caller's arrays while chunk c is copied back
       {
-        const int npc = std::min(chunk, ld - q0);
-        const size_t bytes = sizeof(double) * static_cast<size_t>(npc) * sim_len * RS_O_NVAR;
-        CU(static_cast<cudaError_t>(
-            rs_launch_unpack_out(d_out.as<double>(), ld, sim_len, q0, npc, d_stage.as<double>(), stream)));
-        ++sh.stats.kernel_launches;
+        auto scatter = [&](int q0, int npc, const double* S) {
+          const size_t plane = static_cast<size_t>(npc) * sim_len;
+          parallel_for(npc, nthreads, [&](int q) {
+            const int p = slots[s0 + q0 + q];
+            if (p < 0) return;
+            OutputPointers* op = out[p];
+            double* dst[RS_O_NVAR] = {op->c_TsurfOut, op->c_SnowOut, op->c_WaterOut,
+                                      op->c_IceOut,   op->c_DepositOut, op->c_Ice2Out};
+            for (int v = 0; v < RS_O_NVAR; ++v)
+              std::memcpy(dst[v], S + v * plane + static_cast<size_t>(q) * sim_len, sizeof(double) * sim_len);
+          });
+        };
         CU(cudaEventRecord(ev0, stream));
-        CU(cudaMemcpyAsync(h_stage.p, d_stage.p, bytes, cudaMemcpyDeviceToHost, stream));
+        int cidx = 0, prev_q0 = -1, prev_npc = 0;
+        for (int q0 = 0; q0 < ld; q0 += chunk, ++cidx)
+        {
+          const int npc = std::min(chunk, ld - q0);
+          const int bsel = cidx & 1;
+          const size_t bytes = sizeof(double) * static_cast<size_t>(npc) * sim_len * RS_O_NVAR;
+          CU(static_cast<cudaError_t>(rs_launch_unpack_out(d_out.as<double>(), ld, sim_len, q0, npc, d_st[bsel], stream)));
+          ++sh.stats.kernel_launches;
+          CU(cudaMemcpyAsync(h_st[bsel], d_st[bsel], bytes, cudaMemcpyDeviceToHost, stream));
+          CU(cudaEventRecord(ev_free[bsel], stream));
+          sh.stats.d2h_bytes += bytes;
+          if (prev_q0 >= 0)
+          {
+            // buffer of the previous chunk: its copy was enqueued before this one
+            CU(cudaEventSynchronize(ev_free[bsel ^ 1]));
+            t0 = now_ms();
+            scatter(prev_q0, prev_npc, h_st[bsel ^ 1]);
+            sh.stats.unpack_ms += now_ms() - t0;
+          }
+          prev_q0 = q0;
+          prev_npc = npc;
+        }
         CU(cudaEventRecord(ev1, stream));
+        if (prev_q0 >= 0)
+        {
+          CU(cudaEventSynchronize(ev_free[(cidx - 1) & 1]));
+          t0 = now_ms();
+          scatter(prev_q0, prev_npc, h_st[(cidx - 1) & 1]);
+          sh.stats.unpack_ms += now_ms() - t0;
+        }
         CU(cudaStreamSynchronize(stream));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev0, ev1);
         sh.stats.d2h_ms += ms;
-        sh.stats.d2h_bytes += bytes;
-        t0 = now_ms();
-        const double* S = h_stage.as<double>();
-        const size_t plane = static_cast<size_t>(npc) * sim_len;
-        for (int q = 0; q < npc; ++q)
-        {
-          const int p = slots[s0 + q0 + q];
-          if (p < 0) continue;
-          OutputPointers* op = out[p];
-          double* dst[RS_O_NVAR] = {op->c_TsurfOut, op->c_SnowOut, op->c_WaterOut,
-                                    op->c_IceOut,   op->c_DepositOut, op->c_Ice2Out};
-          for (int v = 0; v < RS_O_NVAR; ++v)
-            std::memcpy(dst[v], S + v * plane + static_cast<size_t>(q) * sim_len, sizeof(double) * sim_len);
-        }
-        sh.stats.unpack_ms += now_ms() - t0;
       }
       CU(cudaMemcpyAsync(h_status.p, d_status.p, sizeof(int) * ld, cudaMemcpyDeviceToHost, stream));
       unsigned long long cnt[RS_CNT_N];
@@ -450,38 +576,12 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
   }
   return RS_OK;
 }
-// Grow-only device work space, one per (device, slot), reused across host-SoA calls so that a
-// steady-state call does no cudaMalloc.
-struct PoolEntry
-{
-  void* p = nullptr;
-  size_t cap = 0;
-};
-std::mutex g_pool_mu;
-std::map<std::pair<int, int>, PoolEntry> g_pool;
-
-cudaError_t pool_get(int device, int slot, size_t bytes, void** out)
-{
-  std::lock_guard<std::mutex> lk(g_pool_mu);
-  PoolEntry& e = g_pool[{device, slot}];
-  if (e.cap < bytes)
-  {
-    if (e.p) cudaFree(e.p);
-    e.p = nullptr;
-    e.cap = 0;
-    cudaError_t rc = cudaMalloc(&e.p, bytes);
-    if (rc != cudaSuccess) return rc;
-    e.cap = bytes;
-  }
-  *out = e.p;
-  return cudaSuccess;
-}
-
 // Points [first, first+count) of a host SoA batch on `device`, pipelined in column chunks over two
 // streams: H2D(chunk c+1) overlaps kernel(chunk c) overlaps D2H(chunk c-1).
 int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* settings,
                        const InputParameters* params)
 {
+  std::lock_guard<std::mutex> device_lock(g_device_mu[sh.device & 63]);
   CU(cudaSetDevice(sh.device));
   RsModel model;
   {
@@ -653,6 +753,7 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
 
 int run_sharded(int npoints, int ngpus, const std::function<int(Shard&)>& fn)
 {
+  const double wall0 = now_ms();
   const int ndev = roadsurf_device_count();
   if (ndev < 1) return fail(RS_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
   if (ngpus <= 0 || ngpus > ndev) ngpus = ndev;
@@ -694,9 +795,11 @@ int run_sharded(int npoints, int ngpus, const std::function<int(Shard&)>& fn)
     g_stats.executed_steps += sh.stats.executed_steps;
     g_stats.kernel_launches += sh.stats.kernel_launches;
     g_stats.groups += sh.stats.groups;
+    g_stats.setup_ms = std::max(g_stats.setup_ms, sh.stats.setup_ms);
     g_launches_total += sh.stats.kernel_launches;
     if (sh.launch.grid) g_launch = sh.launch;
   }
+  g_stats.wall_ms = now_ms() - wall0;
   for (auto& sh : shards)
     if (sh.rc != RS_OK) return fail(sh.rc, sh.err);
   return RS_OK;

@@ -46,7 +46,7 @@ class RsBatchStats(C.Structure):
     _fields_ = [("pack_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("unpack_ms", C.c_double), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("executed_steps", C.c_int64), ("kernel_launches", C.c_int),
-                ("groups", C.c_int)]
+                ("groups", C.c_int), ("wall_ms", C.c_double), ("setup_ms", C.c_double)]
 
 
 class RsLaunchInfo(C.Structure):
@@ -142,18 +142,29 @@ def last_launch():
     return {n: getattr(li, n) for n, _ in RsLaunchInfo._fields_}
 
 
+class PreparedBatch:
+    """The ctypes argument arrays of roadsurf_run_batch for a PointArrays (built once: constructing
+    tens of thousands of ctypes structs in Python takes longer than the GPU run)."""
+
+    def __init__(self, arrays):
+        self.arrays = arrays
+        self.ins = arrays.input_pointers()
+        self.outs = arrays.output_pointers()
+        self.in_ptrs = abi.pointer_arrays(self.ins, abi.InputPointers)
+        self.out_ptrs = abi.pointer_arrays(self.outs, abi.OutputPointers)
+        self.loc_ptrs = abi.pointer_arrays(arrays.local, abi.LocalParameters)
+        self.status = np.zeros(arrays.npoints, dtype=np.int32)
+
+    def run(self, settings, params, ngpus=1):
+        _check(load().roadsurf_run_batch(self.arrays.npoints, self.out_ptrs, self.in_ptrs, C.byref(settings),
+                                         C.byref(params), self.loc_ptrs, int(ngpus),
+                                         self.status.ctypes.data_as(abi.c_int_p)))
+        return self.status
+
+
 def run_batch(arrays, settings, params, ngpus=1):
     """roadsurf_run_batch over a host-layout PointArrays: fills arrays.out, returns status[npoints]."""
-    lib = load()
-    ins = arrays.input_pointers()
-    outs = arrays.output_pointers()
-    in_ptrs = abi.pointer_arrays(ins, abi.InputPointers)
-    out_ptrs = abi.pointer_arrays(outs, abi.OutputPointers)
-    loc_ptrs = abi.pointer_arrays(arrays.local, abi.LocalParameters)
-    status = np.zeros(arrays.npoints, dtype=np.int32)
-    _check(lib.roadsurf_run_batch(arrays.npoints, out_ptrs, in_ptrs, C.byref(settings), C.byref(params),
-                                  loc_ptrs, int(ngpus), status.ctypes.data_as(abi.c_int_p)))
-    return status
+    return PreparedBatch(arrays).run(settings, params, ngpus)
 
 
 def run_host_soa(settings, params, forcing, time_fields, local, out, record_step=None, horizons=None,

@@ -329,3 +329,29 @@ def test_tma_staged_forcing_ring_gives_identical_results(rslib):
         assert np.array_equal(st0, st1)
         for k in arrays.out:
             assert np.array_equal(arrays.out[k], staged.out[k]), (kw, k)
+
+
+def test_runsimulation_is_reentrant_from_host_threads(rslib, oracle):
+    """The reference is called concurrently from N host threads, one point each
+    (examples/example1/src/roadrunner.cpp:454-496); the drop-in must give the same answers."""
+    import threading
+    arrays, settings, params, _ = synth.make_case(24, 3, seed=42, analysis_hours=2, use_coupling=1,
+                                                   use_relaxation=1, settings_kw=dict(coupling_minutes=60))
+    ref = arrays.copy()
+    rslib.run_batch(ref, settings, params)
+    errors = []
+
+    def work(lo, hi):
+        try:
+            for p in range(lo, hi):
+                rslib.runsimulation(arrays, settings, params, point=p)
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+    threads = [threading.Thread(target=work, args=(k * 6, k * 6 + 6)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    for k in arrays.out:
+        assert np.array_equal(arrays.out[k], ref.out[k]), k
