@@ -264,13 +264,23 @@ typedef struct RsDeviceBatch
   int out_stride;             /* write step i (1-based) when (i-1) % out_stride == 0 */
   int n_out;                  /* ceil(sim_len / out_stride) */
   int* status;                /* [ld] status words (written) */
-  double* state;              /* optional [RS_STATE_NPLANES(NLayers)][ld] end-of-run state dump,
-                                 or NULL */
+  double* state;              /* optional [RS_STATE_NPLANES(NLayers)][ld]: full per-point state, written
+                                 at the end of every launch, read when step_begin > 1; or NULL */
   double* scratch;            /* [RS_SCRATCH_NPLANES(NLayers)][ld] work space; required when the
                                  model has use_coupling == 1, else may be NULL */
   unsigned long long* counters; /* optional [RS_CNT_N] device counters (accumulated), or NULL */
   double* solar;              /* [sim_len][4] work space: per-step solar table (time-only part of
                                  src/SunPosition.f90), filled by the library at every launch */
+  /* Time chunking (all 0 = one launch for the whole run).  A launch runs the model steps
+   * [step_begin, step_end] (1-based, inclusive).  With step_begin > 1 the per-point state is loaded
+   * from `state` (as written by the launch that ended at step_begin - 1; `status`, `scratch` and
+   * `counters` must be the same buffers), so a run may be split into chunks whose forcing is streamed
+   * through HBM; results are bit-identical to a single launch.  A chunk must contain a warp's whole
+   * coupling window [start, end + 1] or none of it (else RS_ST_BAD_WINDOW). */
+  int step_begin;
+  int step_end;
+  int forcing_step0;          /* forcing_mode 0: model step of forcing record 0 (0 -> 1) */
+  int out_slot0;              /* output slot (step-1)/out_stride stored at out[:, 0, :] */
 } RsDeviceBatch;
 
 enum
@@ -282,8 +292,9 @@ enum
   RS_CNT_N = 8
 };
 
-/* Number of fp64 planes of the end-of-run state dump for a given NLayers. */
-#define RS_STATE_NPLANES(nlayers) ((nlayers) + 2 + 12)
+/* Number of fp64 planes of the per-point state for a given NLayers: Tmp(0:N+1), 10 surface scalars,
+ * 3 relaxation latches, 5 radiation-coupling scalars, 1 flag word. */
+#define RS_STATE_NPLANES(nlayers) ((nlayers) + 2 + 19)
 /* Number of fp64 planes of the coupling work space (window snapshot + bracket scalars). */
 #define RS_SCRATCH_NPLANES(nlayers) (2 * (nlayers) + 16)
 

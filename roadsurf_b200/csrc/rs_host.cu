@@ -485,6 +485,10 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
       a.out_stride = 1;
       a.n_out = sim_len;
       a.forcing_mode = 0;
+      a.step_begin = 1;
+      a.step_end = sim_len;
+      a.forcing_step0 = 1;
+      a.out_slot0 = 0;
       a.forcing = d_forcing.as<double>();
       a.tf = d_tf.as<int>();
       a.local = d_local.as<double>();
@@ -709,6 +713,10 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     a.out_stride = b->out_stride;
     a.n_out = n_out;
     a.forcing_mode = b->forcing_mode;
+    a.step_begin = 1;
+    a.step_end = b->sim_len;
+    a.forcing_step0 = 1;
+    a.out_slot0 = 0;
     a.forcing = d_forcing[s];
     a.record_step = d_rs;
     a.tf = d_tf;
@@ -861,14 +869,26 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   }
   if (b->ld < 32 || b->ld % 32 != 0 || b->npoints < 0 || b->npoints > b->ld)
     return fail(RS_ERR_BAD_ARGUMENT, "ld must be a positive multiple of 32 and >= npoints");
-  if (b->sim_len < 1 || b->out_stride < 1 || b->n_out != (b->sim_len + b->out_stride - 1) / b->out_stride)
+  const int step_begin = b->step_begin > 0 ? b->step_begin : 1;
+  const int step_end = b->step_end > 0 ? b->step_end : b->sim_len;
+  const int forcing_step0 = b->forcing_step0 > 0 ? b->forcing_step0 : 1;
+  if (b->sim_len < 1 || b->out_stride < 1 || b->n_out < 1)
     return fail(RS_ERR_BAD_ARGUMENT, "bad sim_len / out_stride / n_out");
+  if (step_begin > step_end || step_end > b->sim_len || forcing_step0 > step_begin || b->out_slot0 < 0)
+    return fail(RS_ERR_BAD_ARGUMENT, "bad step_begin / step_end / forcing_step0 / out_slot0");
+  {
+    const int first_slot = (step_begin - 1 + b->out_stride - 1) / b->out_stride, last_slot = (step_end - 1) / b->out_stride;
+    if (last_slot >= first_slot && (first_slot < b->out_slot0 || last_slot - b->out_slot0 >= b->n_out))
+      return fail(RS_ERR_BAD_ARGUMENT, "out tensor does not cover the output slots of [step_begin, step_end]");
+  }
+  if (step_begin > 1 && !b->state) return fail(RS_ERR_BAD_ARGUMENT, "step_begin > 1 needs batch->state from the previous chunk");
   if (b->nvar != RS_F_NVAR && b->nvar != RS_F_NVAR_DEPTH) return fail(RS_ERR_BAD_ARGUMENT, "nvar must be 11 or 12");
   if (!b->forcing || !b->time_fields || !b->local || !b->out || !b->status || !b->solar)
     return fail(RS_ERR_BAD_ARGUMENT, "null device pointer in batch");
   if (b->forcing_mode == 0)
   {
-    if (b->n_records != b->sim_len) return fail(RS_ERR_BAD_ARGUMENT, "forcing_mode 0 needs n_records == sim_len");
+    if (b->n_records < step_end - forcing_step0 + 1)
+      return fail(RS_ERR_BAD_ARGUMENT, "forcing_mode 0 needs n_records >= step_end - forcing_step0 + 1");
   }
   else if (b->forcing_mode == 1)
   {
@@ -887,6 +907,10 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   a.out_stride = b->out_stride;
   a.n_out = b->n_out;
   a.forcing_mode = b->forcing_mode;
+  a.step_begin = step_begin;
+  a.step_end = step_end;
+  a.forcing_step0 = forcing_step0;
+  a.out_slot0 = b->out_slot0;
   a.forcing = b->forcing;
   a.record_step = b->record_step;
   a.tf = b->time_fields;

@@ -13,6 +13,9 @@
 struct RsArgs
 {
   int npoints, ld, sim_len, n_records, nvar, out_stride, n_out, forcing_mode;
+  int step_begin, step_end;   // model steps this launch runs (1-based, inclusive)
+  int forcing_step0;          // full-resolution mode: model step of forcing record 0
+  int out_slot0;              // global output slot stored at out[:, 0, :]
   const double* forcing;
   const int* record_step;
   const int* tf;            // [6][sim_len]

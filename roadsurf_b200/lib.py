@@ -35,7 +35,7 @@ EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roa
 
 
 def state_nplanes(nlayers):
-    return nlayers + 2 + 12
+    return nlayers + 2 + 19
 
 
 def scratch_nplanes(nlayers):
@@ -62,7 +62,8 @@ class RsDeviceBatch(C.Structure):
                 ("local", C.c_void_p), ("horizons", C.c_void_p), ("out", C.c_void_p),
                 ("out_stride", C.c_int), ("n_out", C.c_int), ("status", C.c_void_p),
                 ("state", C.c_void_p), ("scratch", C.c_void_p), ("counters", C.c_void_p),
-                ("solar", C.c_void_p)]
+                ("solar", C.c_void_p), ("step_begin", C.c_int), ("step_end", C.c_int),
+                ("forcing_step0", C.c_int), ("out_slot0", C.c_int)]
 
 
 class RsHostBatch(C.Structure):
@@ -232,21 +233,27 @@ class DeviceBatch:
         self.counters = torch.zeros(CNT_N, dtype=torch.int64, device=device)
         self.solar = torch.zeros((self.sim_len, 4), **f64)
 
-    def descriptor(self):
+    def descriptor(self, step_begin=0, step_end=0, forcing=None, forcing_step0=0, out=None, out_slot0=0):
         def ptr(t):
             return None if t is None else t.data_ptr()
-        return RsDeviceBatch(npoints=self.npoints, ld=self.ld, sim_len=self.sim_len,
-                             forcing_mode=1 if self.coarse else 0, n_records=self.n_records,
-                             nvar=self.nvar, forcing=ptr(self.forcing), record_step=ptr(self.record_step),
+        forcing = self.forcing if forcing is None else forcing
+        out = self.out if out is None else out
+        n_records = forcing.shape[0]
+        return RsDeviceBatch(step_begin=step_begin, step_end=step_end, forcing_step0=forcing_step0,
+                             out_slot0=out_slot0, npoints=self.npoints, ld=self.ld, sim_len=self.sim_len,
+                             forcing_mode=1 if self.coarse else 0, n_records=n_records,
+                             nvar=self.nvar, forcing=ptr(forcing), record_step=ptr(self.record_step),
                              time_fields=ptr(self.time_fields), local=ptr(self.local),
-                             horizons=ptr(self.horizons), out=ptr(self.out), out_stride=self.out_stride,
-                             n_out=self.n_out, status=ptr(self.status), state=ptr(self.state),
+                             horizons=ptr(self.horizons), out=ptr(out), out_stride=self.out_stride,
+                             n_out=out.shape[1], status=ptr(self.status), state=ptr(self.state),
                              scratch=ptr(self.scratch), counters=ptr(self.counters), solar=ptr(self.solar))
 
-    def run(self, stream=None):
-        """Asynchronous launch on `stream` (a torch.cuda.Stream; default: the current stream)."""
+    def run(self, stream=None, **chunk):
+        """Asynchronous launch on `stream` (a torch.cuda.Stream; default: the current stream).
+        Keyword arguments select a time chunk: step_begin, step_end, forcing (tensor holding only the
+        chunk's records), forcing_step0, out (tensor holding only the chunk's slots), out_slot0."""
         st = stream if stream is not None else self.torch.cuda.current_stream()
-        desc = self.descriptor()
+        desc = self.descriptor(**chunk)
         _check(load().roadsurf_run_device(C.byref(desc), C.c_void_p(st.cuda_stream)))
 
     # ---- helpers to fill the batch from host-layout data (tests, small cases) -----------------

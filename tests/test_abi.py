@@ -29,7 +29,7 @@ int main(void) {
   O(LocalParameters, sky_view); O(LocalParameters, InitLenI);
   S(RsDeviceBatch); S(RsBatchStats); S(RsLaunchInfo);
   O(RsDeviceBatch, forcing); O(RsDeviceBatch, out_stride); O(RsDeviceBatch, scratch); O(RsDeviceBatch, counters);
-  O(RsDeviceBatch, solar);
+  O(RsDeviceBatch, solar); O(RsDeviceBatch, step_begin); O(RsDeviceBatch, out_slot0);
   return 0;
 }
 """

@@ -355,3 +355,62 @@ def test_runsimulation_is_reentrant_from_host_threads(rslib, oracle):
     assert not errors
     for k in arrays.out:
         assert np.array_equal(arrays.out[k], ref.out[k]), k
+
+
+def test_time_chunked_launches_resume_from_soa_state(rslib):
+    """A run split into time chunks (state written as SoA planes at the end of a launch and loaded
+    by the next one; each chunk given only its own slice of forcing and of the output tensor) is
+    bit-identical to the single launch, with the coupling window inside the first chunk."""
+    import torch
+    arrays, settings, params, _ = synth.make_case(96, 8, seed=43, analysis_hours=4, use_coupling=1,
+                                                   use_relaxation=1)
+    rslib.set_model(settings, params)
+    whole = rslib.DeviceBatch(96, arrays.sim_len, horizons=True, coupling=True, state=True)
+    whole.load_point_arrays(arrays)
+    whole.run()
+    torch.cuda.synchronize()
+    want, want_status = whole.out.clone(), whole.status.clone()
+    want_steps = int(whole.counters[rslib.CNT_EXECUTED_STEPS])
+
+    chunked = rslib.DeviceBatch(96, arrays.sim_len, horizons=True, coupling=True, state=True)
+    chunked.load_point_arrays(arrays)
+    chunked.out.fill_(123.0)
+    cend = arrays.local[0].couplingIndexI
+    bounds = [1, cend + 40, cend + 700, arrays.sim_len + 1]       # chunk k = steps [b[k], b[k+1]-1]
+    got = torch.empty_like(want)
+    for k in range(3):
+        b, e = bounds[k], bounds[k + 1] - 1
+        forcing = chunked.forcing[b - 1:e].clone()                # only this chunk's records
+        out = torch.full((rslib.O_NVAR, e - b + 1, chunked.ld), 55.0, dtype=torch.float64, device="cuda")
+        chunked.run(step_begin=b, step_end=e, forcing=forcing, forcing_step0=b, out=out, out_slot0=b - 1)
+        torch.cuda.synchronize()
+        got[:, b - 1:e] = out
+    assert torch.equal(got, want)
+    assert torch.equal(chunked.status, want_status)
+    assert int(chunked.counters[rslib.CNT_EXECUTED_STEPS]) == want_steps
+    assert torch.equal(chunked.state, whole.state)
+
+    # a chunk boundary inside the coupling window is refused per point, not silently accepted
+    bad = rslib.DeviceBatch(96, arrays.sim_len, horizons=True, coupling=True, state=True)
+    bad.load_point_arrays(arrays)
+    bad.run(step_begin=1, step_end=cend - 10)
+    torch.cuda.synchronize()
+    assert (bad.status[:96].cpu().numpy() & rslib.ST_BAD_WINDOW).all()
+
+    # coarse forcing + strided output, two chunks
+    arrays2, settings2, params2, rec = synth.make_case(64, 6, seed=44)
+    rslib.set_model(settings2, params2)
+
+    def coarse_batch():
+        db = rslib.DeviceBatch(64, arrays2.sim_len, n_records=rec.nrec, coarse=True, horizons=True,
+                               out_stride=120, state=True)
+        db.load_records(rec)
+        db.time_fields.copy_(torch.from_numpy(arrays2.time))
+        db.load_local(arrays2.local, arrays2.local_horizons)
+        return db
+    one, two = coarse_batch(), coarse_batch()
+    one.run()
+    two.run(step_begin=1, step_end=300)
+    two.run(step_begin=301, step_end=arrays2.sim_len)
+    torch.cuda.synchronize()
+    assert torch.equal(one.out, two.out) and torch.equal(one.state, two.state)
