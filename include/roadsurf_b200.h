@@ -354,7 +354,9 @@ double roadsurf_measure_fp64_tflops(int iterations);
 /* Run-time options.  "forcing_staging": 1 = in full-resolution mode stage the forcing of every warp
  * through a ring of shared-memory tiles filled by TMA bulk copies a few steps ahead, 0 = direct
  * coalesced read-only loads (default; measured 3-6 % faster on B200).  The default can
- * also be set with the environment variable ROADSURF_B200_FORCING_STAGING=1.  Results are identical. */
+ * also be set with the environment variable ROADSURF_B200_FORCING_STAGING=1.  Results are identical.
+ * "max_points_per_device_batch": cap on the points roadsurf_run_batch puts into one device batch
+ * (0 = bounded by free device memory only); batches beyond it are processed one after another. */
 int roadsurf_set_option(const char* name, int value);
 
 /* Arithmetic self-test on the current device: the kernel's branch-free reciprocal, division and

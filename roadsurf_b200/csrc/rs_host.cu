@@ -33,6 +33,7 @@ int g_launches_total = 0;
 // Run-time options (roadsurf_set_option).  forcing_staging: 1 = full-resolution forcing through the
 // per-warp TMA ring in shared memory, 0 = direct read-only loads (default: measured faster).
 int g_opt_staging = -1;
+int g_opt_max_slots = 0;  // test hook: cap on points per device batch in roadsurf_run_batch (0 = memory bound)
 int opt_staging()
 {
   if (g_opt_staging < 0)
@@ -309,6 +310,7 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
     size_t budget = static_cast<size_t>(free_b * 0.80);
     size_t max_slots = budget / per_slot / 32 * 32;
     if (max_slots < 32) return fail(RS_ERR_CUDA, "not enough device memory for one warp of points");
+    if (g_opt_max_slots > 0) max_slots = std::min<size_t>(max_slots, (g_opt_max_slots + 31) / 32 * 32);
     // staging chunk: <= 192 MiB of pinned memory per direction
     const size_t stage_budget = 192ull << 20;
     int chunk = static_cast<int>(std::max<size_t>(32, stage_budget / (sizeof(double) * sim_len * nvar) / 32 * 32));
@@ -973,6 +975,11 @@ int roadsurf_set_option(const char* name, int value)
   if (name && std::strcmp(name, "forcing_staging") == 0)
   {
     g_opt_staging = value ? 1 : 0;
+    return RS_OK;
+  }
+  if (name && std::strcmp(name, "max_points_per_device_batch") == 0)
+  {
+    g_opt_max_slots = value > 0 ? value : 0;
     return RS_OK;
   }
   return fail(RS_ERR_BAD_ARGUMENT, "unknown option");

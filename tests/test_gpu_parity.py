@@ -414,3 +414,37 @@ def test_time_chunked_launches_resume_from_soa_state(rslib):
     two.run(step_begin=301, step_end=arrays2.sim_len)
     torch.cuda.synchronize()
     assert torch.equal(one.out, two.out) and torch.equal(one.state, two.state)
+
+
+def test_batches_larger_than_the_device_budget_are_split(rslib):
+    """roadsurf_run_batch processes a batch in several device batches when it does not fit the
+    memory budget; forced here with a 64-point cap.  Mixed coupling windows keep their warp padding."""
+    arrays, settings, params, _ = synth.make_case(300, 4, seed=45, analysis_hours=4, use_coupling=1,
+                                                   use_relaxation=1, settings_kw=dict(coupling_minutes=120))
+    for p in range(0, 300, 3):
+        arrays.local[p].couplingIndexI = 400 + (p % 7)
+    split = arrays.copy()
+    st0 = rslib.run_batch(arrays, settings, params)
+    try:
+        rslib.set_option("max_points_per_device_batch", 64)
+        st1 = rslib.run_batch(split, settings, params)
+    finally:
+        rslib.set_option("max_points_per_device_batch", 0)
+    assert np.array_equal(st0, st1)
+    for k in arrays.out:
+        assert np.array_equal(arrays.out[k], split.out[k]), k
+
+
+def test_multi_gpu_sharding_inside_the_library(rslib):
+    """ngpus > 1: contiguous point shards on several devices from the library's own host threads.
+    Needs two visible GPUs; bit-identical to the single-GPU result."""
+    if rslib.load().roadsurf_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    arrays, settings, params, _ = synth.make_case(333, 4, seed=46, analysis_hours=4, use_coupling=1,
+                                                   use_relaxation=1, settings_kw=dict(coupling_minutes=120))
+    two = arrays.copy()
+    st0 = rslib.run_batch(arrays, settings, params, ngpus=1)
+    st1 = rslib.run_batch(two, settings, params, ngpus=2)
+    assert np.array_equal(st0, st1)
+    for k in arrays.out:
+        assert np.array_equal(arrays.out[k], two.out[k]), k
