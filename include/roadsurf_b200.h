@@ -175,6 +175,21 @@ int roadsurf_run_batch(int npoints, OutputPointers* const* out, const InputPoint
                        const InputSettings* settings, const InputParameters* params,
                        const LocalParameters* const* local, int ngpus, int* status);
 
+/* Host-side preparation of a batch: what the example's read_input derives per point before it calls
+ * runsimulation (examples/example1/src/roadrunner.cpp:157-278).  For every point p:
+ *   - screens the required inputs (tair, Rhz, prec, SW, LW, VZ: NaN or < -9000 at any step) ->
+ *     ok[p] = 0 and the point is left untouched (read_input returns success = false);
+ *   - InitLenI = 1 + forecast_step; with use_relaxation == 1 and latest_obs_index[p] > -1
+ *     (GetLatestObsIndex, JsonSource.cpp:397-414): InitLenI = that index and the relaxation targets
+ *     are the inputs at that (0-based) index, else the targets are -9999.9;
+ *   - with use_coupling == 1: the latest valid TSurfObs index i (not NaN, >= -100); if
+ *     i >= coupling_minutes*60/DTSecs: couplingTsurf = TSurfObs[i], couplingIndexI = i and
+ *     TSurfObs is blanked to -9999.9 over (i - span, i] IN THE CALLER'S ARRAY, as read_input does.
+ * latest_obs_index and ok may be NULL.  Pure host code: works without a GPU.  Returns RS_OK. */
+int roadsurf_read_input_derive(int npoints, const InputPointers* const* in, const InputSettings* settings,
+                               int forecast_step, const int* latest_obs_index, LocalParameters* const* local,
+                               int* ok);
+
 /* Statistics of the most recent roadsurf_run_batch on this thread. */
 typedef struct RsBatchStats
 {

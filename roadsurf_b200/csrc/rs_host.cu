@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -499,10 +500,12 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
       a.out = d_out.as<double>();
       a.status = d_status.as<int>();
       a.scratch = model.use_coupling ? d_scratch.as<double>() : nullptr;
-      a.counters = d_counters.as<unsigned long long>();
+      RsArgsCold ac;
+      ac.state = nullptr;
+      ac.counters = d_counters.as<unsigned long long>();
       CU(cudaEventRecord(ev0, stream));
       CU(static_cast<cudaError_t>(
-          rs_launch_run(&a, nl, opt_staging(), stream, &sh.launch.grid, &sh.launch.block,
+          rs_launch_run(&a, &ac, nl, opt_staging(), stream, &sh.launch.grid, &sh.launch.block,
                         &sh.launch.regs_per_thread, &sh.launch.smem_bytes)));
       CU(cudaEventRecord(ev1, stream));
       ++sh.stats.kernel_launches;
@@ -728,9 +731,11 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     a.out = d_out[s];
     a.status = d_status[s];
     a.scratch = d_scratch[s];
-    a.counters = d_counters;
+    RsArgsCold ac;
+    ac.state = nullptr;
+    ac.counters = d_counters;
     CU(static_cast<cudaError_t>(
-        rs_launch_run(&a, nl, opt_staging(), st, &sh.launch.grid, &sh.launch.block, &sh.launch.regs_per_thread,
+        rs_launch_run(&a, &ac, nl, opt_staging(), st, &sh.launch.grid, &sh.launch.block, &sh.launch.regs_per_thread,
                       &sh.launch.smem_bytes)));
     ++sh.stats.kernel_launches;
     sh.launch.nlayers = nl;
@@ -921,14 +926,15 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   a.solar = b->solar;
   a.out = b->out;
   a.status = b->status;
-  a.state = b->state;
   a.scratch = b->scratch;
-  a.counters = b->counters;
+  RsArgsCold ac;
+  ac.state = b->state;
+  ac.counters = b->counters;
   RsLaunchInfo li;
   std::memset(&li, 0, sizeof li);
   CU(static_cast<cudaError_t>(rs_launch_solar(b->time_fields, b->sim_len, b->solar, stream)));
   ++g_launches_total;
-  CU(static_cast<cudaError_t>(rs_launch_run(&a, m.nlayers, opt_staging(), stream, &li.grid, &li.block,
+  CU(static_cast<cudaError_t>(rs_launch_run(&a, &ac, m.nlayers, opt_staging(), stream, &li.grid, &li.block,
                                             &li.regs_per_thread, &li.smem_bytes)));
   li.nlayers = m.nlayers;
   li.forcing_mode = b->forcing_mode;
@@ -1002,6 +1008,55 @@ void roadsurf_last_launch(RsLaunchInfo* info)
     *info = g_launch;
     info->launches_total = g_launches_total;
   }
+}
+
+int roadsurf_read_input_derive(int npoints, const InputPointers* const* in, const InputSettings* settings,
+                               int forecast_step, const int* latest_obs_index, LocalParameters* const* local,
+                               int* ok)
+{
+  if (npoints < 0 || !settings || (npoints > 0 && (!in || !local))) return fail(RS_ERR_BAD_ARGUMENT, "null argument");
+  const int sim_len = settings->SimLen;
+  const int span = static_cast<int>(settings->coupling_minutes * 60 / settings->DTSecs);
+  auto missing = [](double x) { return std::isnan(x) || x < -9000; };  // roadrunner.cpp:40-43
+  parallel_for(npoints, host_threads(), [&](int p) {
+    const InputPointers* ip = in[p];
+    LocalParameters* lp = local[p];
+    const int n = std::min(sim_len, ip->inputLen);
+    bool good = true;
+    for (int t = 0; t < n && good; ++t)
+      good = !(missing(ip->c_tair[t]) || missing(ip->c_Rhz[t]) || missing(ip->c_prec[t]) || missing(ip->c_SW[t]) ||
+               missing(ip->c_LW[t]) || missing(ip->c_VZ[t]));
+    if (ok) ok[p] = good ? 1 : 0;
+    if (!good) return;
+    lp->InitLenI = 1 + forecast_step;
+    if (settings->use_relaxation == 1)
+    {
+      lp->tair_relax = lp->VZ_relax = lp->RH_relax = -9999.9;
+      const int last = latest_obs_index ? latest_obs_index[p] : -9999;
+      if (last > -1 && last < n)
+      {
+        lp->InitLenI = last;
+        lp->tair_relax = ip->c_tair[last];
+        lp->VZ_relax = ip->c_VZ[last];
+        lp->RH_relax = ip->c_Rhz[last];
+      }
+    }
+    if (settings->use_coupling == 1)
+    {
+      lp->couplingTsurf = -9999.9;
+      lp->couplingIndexI = -9999;
+      double* obs = ip->c_TSurfObs;
+      int i = n - 1;
+      while (i >= 0 && (missing(obs[i]) || obs[i] < -100)) --i;
+      if (i >= span)
+      {
+        lp->couplingTsurf = obs[i];
+        lp->couplingIndexI = i;
+        for (int j = i; j > i - span; --j) obs[j] = -9999.9;
+      }
+    }
+  });
+  return RS_OK;
 }
 
 void roadsurf_last_batch_stats(RsBatchStats* stats)

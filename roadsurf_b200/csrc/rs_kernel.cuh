@@ -13,9 +13,6 @@
 struct RsArgs
 {
   int npoints, ld, sim_len, n_records, nvar, out_stride, n_out, forcing_mode;
-  int step_begin, step_end;   // model steps this launch runs (1-based, inclusive)
-  int forcing_step0;          // full-resolution mode: model step of forcing record 0
-  int out_slot0;              // global output slot stored at out[:, 0, :]
   const double* forcing;
   const int* record_step;
   const int* tf;            // [6][sim_len]
@@ -24,15 +21,25 @@ struct RsArgs
   const double* solar;      // [sim_len][4] per-step solar table (rs_launch_solar)
   double* out;              // [6][n_out][ld]
   int* status;
-  double* state;
   double* scratch;          // [RS_SCRATCH_NPLANES(N)][ld] or null
-  unsigned long long* counters;
+  int step_begin, step_end;   // model steps this launch runs (1-based, inclusive)
+  int forcing_step0;          // full-resolution mode: model step of forcing record 0
+  int out_slot0;              // global output slot stored at out[:, 0, :]
+  // Kept at 120 bytes on purpose: with a 136-byte parameter struct nvcc 12.9 stops scalarising it
+  // and the 128-thread full-resolution kernel picks up 200+ bytes of local-memory traffic per step.
+  // Pointers touched only before / after the time loop live in RsArgsCold.
+};
+
+struct RsArgsCold
+{
+  double* state;                 // [RS_STATE_NPLANES(N)][ld] or null
+  unsigned long long* counters;  // [RS_CNT_N] or null
 };
 
 // Host-callable launchers (rs_kernel.cu).  Return a cudaError_t as int.
 int rs_upload_model(const RsModel* m);
 int rs_launch_solar(const int* tf, int sim_len, double* table, void* stream);
-int rs_launch_run(const RsArgs* a, int nlayers, int staged, void* stream, int* grid, int* block, int* regs,
+int rs_launch_run(const RsArgs* a, const RsArgsCold* cold, int nlayers, int staged, void* stream, int* grid, int* block, int* regs,
                   int* smem);
 int rs_launch_transpose_to_soa(const double* src, long long src_ld, int npoints, int n, double* dst,
                                int ld, void* stream);

@@ -27,7 +27,7 @@ O_NVAR = 6
 CNT_EXECUTED_STEPS, CNT_BL_ITERATIONS, CNT_COUPLING_PASSES, CNT_FAILED_POINTS, CNT_N = 0, 1, 2, 3, 8
 
 EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roadsurf_run_batch",
-           "roadsurf_run_host_soa",
+           "roadsurf_run_host_soa", "roadsurf_read_input_derive",
            "roadsurf_last_batch_stats", "roadsurf_set_model", "roadsurf_run_device",
            "roadsurf_transpose_to_soa", "roadsurf_transpose_from_soa", "roadsurf_fill",
            "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_set_option", "roadsurf_last_launch",
@@ -102,6 +102,8 @@ def load():
     lib.roadsurf_run_batch.restype = C.c_int
     lib.roadsurf_run_host_soa.argtypes = [P(RsHostBatch), P(IS), P(IPa), C.c_int]
     lib.roadsurf_run_host_soa.restype = C.c_int
+    lib.roadsurf_read_input_derive.argtypes = [C.c_int, P(P(IP)), P(IS), C.c_int, P(C.c_int), P(P(LP)), P(C.c_int)]
+    lib.roadsurf_read_input_derive.restype = C.c_int
     lib.roadsurf_last_batch_stats.argtypes = [P(RsBatchStats)]
     lib.roadsurf_set_model.argtypes = [P(IS), P(IPa)]
     lib.roadsurf_set_model.restype = C.c_int
@@ -327,3 +329,19 @@ def selftest_arith(n=200_000_000, seed=12345):
 
 def set_option(name, value):
     _check(load().roadsurf_set_option(name.encode(), int(value)))
+
+
+def read_input_derive(arrays, settings, forecast_step, latest_obs_index=None):
+    """roadsurf_read_input_derive over a PointArrays (host only; fills arrays.local, blanks TSurfObs over
+    the coupling window).  Returns ok[npoints]."""
+    ins = arrays.input_pointers()
+    in_ptrs = abi.pointer_arrays(ins, abi.InputPointers)
+    loc_ptrs = abi.pointer_arrays(arrays.local, abi.LocalParameters)
+    ok = np.zeros(arrays.npoints, dtype=np.int32)
+    lat = None
+    if latest_obs_index is not None:
+        lat = np.ascontiguousarray(latest_obs_index, dtype=np.int32)
+    _check(load().roadsurf_read_input_derive(arrays.npoints, in_ptrs, C.byref(settings), int(forecast_step),
+                                             None if lat is None else lat.ctypes.data_as(abi.c_int_p), loc_ptrs,
+                                             ok.ctypes.data_as(abi.c_int_p)))
+    return ok

@@ -321,11 +321,12 @@ def test_tma_staged_forcing_ring_gives_identical_results(rslib):
         try:
             rslib.set_option("forcing_staging", 1)
             st1 = rslib.run_batch(staged, settings, params)
-            assert rslib.last_launch()["smem_bytes"] > 0
+            smem_staged = rslib.last_launch()["smem_bytes"]
         finally:
             rslib.set_option("forcing_staging", 0)
         st0 = rslib.run_batch(arrays, settings, params)
-        assert rslib.last_launch()["smem_bytes"] == 0
+        # the staged variant adds the per-warp tile ring to the per-lane cold-state slots
+        assert smem_staged > rslib.last_launch()["smem_bytes"] > 0
         assert np.array_equal(st0, st1)
         for k in arrays.out:
             assert np.array_equal(arrays.out[k], staged.out[k]), (kw, k)

@@ -146,3 +146,31 @@ def test_default_settings_and_copy_semantics():
     assert (s.DTSecs, s.NLayers, s.coupling_minutes, s.couplingEffectReduction, s.outputStep) == (
         30.0, 15, 180, 14400.0, 60)
     assert s.force_tsurf == 0 and s.tsurfOutputDepth < 0
+
+
+def test_library_read_input_derive_matches_the_example_logic():
+    """roadsurf_read_input_derive (C, host only, no GPU needed) against the Python restatement of
+    examples/example1/src/roadrunner.cpp:157-278 used by the synthetic cases."""
+    from roadsurf_b200 import lib
+    arrays, settings, params, rec = synth.make_case(40, 6, seed=8, analysis_hours=6, use_coupling=1,
+                                                    use_relaxation=1)
+    # undo the derivation made by make_case: rebuild the un-derived inputs from the records
+    fresh, settings, params = synth.case_from_records(rec, 6, 6, 1, 1)
+    want_local = [(lp.InitLenI, lp.tair_relax, lp.VZ_relax, lp.RH_relax, lp.couplingIndexI, lp.couplingTsurf)
+                  for lp in fresh.local]
+    want_obs = fresh.TSurfObs.copy()
+    raw, _, _ = synth.case_from_records(rec, 6, 6, 0, 0)       # no derivation: use flags are off
+    raw.TSurfObs[3, :] = -9999.9                                # a point without any surface observation
+    raw.tair[5, 100] = float("nan")                             # a point with missing required input
+    ok = lib.read_input_derive(raw, settings, 720, latest_obs_index=np.full(40, 721))
+    assert ok[5] == 0 and ok.sum() == 39
+    for p in range(40):
+        lp = raw.local[p]
+        got = (lp.InitLenI, lp.tair_relax, lp.VZ_relax, lp.RH_relax, lp.couplingIndexI, lp.couplingTsurf)
+        if p == 5:
+            continue
+        if p == 3:
+            assert lp.couplingIndexI == -9999 and lp.couplingTsurf == -9999.9 and lp.InitLenI == 721
+            continue
+        assert got == want_local[p], p
+        assert np.array_equal(raw.TSurfObs[p], want_obs[p]), p
