@@ -366,6 +366,11 @@ int roadsurf_fill(double* dst, int64_t n, double value, void* stream);
  * register-resident DFMA kernel; used as the fp64 roofline denominator by bench.py. */
 double roadsurf_measure_fp64_tflops(int iterations);
 
+/* roadsurf_run_batch and roadsurf_run_host_soa keep their device and pinned-host work buffers between
+ * calls (allocation costs more than a run).  This releases them; they are re-created on demand.  Must
+ * not be called while another thread is inside one of those entry points. */
+void roadsurf_release_workspace(void);
+
 /* Run-time options.  "forcing_staging": 1 = in full-resolution mode stage the forcing of every warp
  * through a ring of shared-memory tiles filled by TMA bulk copies a few steps ahead, 0 = direct
  * coalesced read-only loads (default; measured 3-6 % faster on B200).  The default can

@@ -29,20 +29,22 @@ thread_local RsBatchStats g_stats;
 thread_local RsLaunchInfo g_launch;
 std::mutex g_model_mu;
 std::map<int, RsModel> g_models;  // device -> model currently in its constant memory
-int g_launches_total = 0;
+std::atomic<int> g_launches_total{0};
 
 // Run-time options (roadsurf_set_option).  forcing_staging: 1 = full-resolution forcing through the
 // per-warp TMA ring in shared memory, 0 = direct read-only loads (default: measured faster).
-int g_opt_staging = -1;
-int g_opt_max_slots = 0;  // test hook: cap on points per device batch in roadsurf_run_batch (0 = memory bound)
+std::atomic<int> g_opt_staging{-1};
+std::atomic<int> g_opt_max_slots{0};  // test hook: cap on points per device batch in roadsurf_run_batch (0 = memory bound)
 int opt_staging()
 {
-  if (g_opt_staging < 0)
+  int v = g_opt_staging.load();
+  if (v < 0)
   {
     const char* e = std::getenv("ROADSURF_B200_FORCING_STAGING");
-    g_opt_staging = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '1') ? 1 : 0;
+    g_opt_staging.store(v);
   }
-  return g_opt_staging;
+  return v;
 }
 
 int fail(int code, const std::string& msg)
@@ -311,7 +313,7 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
     size_t budget = static_cast<size_t>(free_b * 0.80);
     size_t max_slots = budget / per_slot / 32 * 32;
     if (max_slots < 32) return fail(RS_ERR_CUDA, "not enough device memory for one warp of points");
-    if (g_opt_max_slots > 0) max_slots = std::min<size_t>(max_slots, (g_opt_max_slots + 31) / 32 * 32);
+    if (const int cap = g_opt_max_slots.load()) max_slots = std::min<size_t>(max_slots, (cap + 31) / 32 * 32);
     // staging chunk: <= 192 MiB of pinned memory per direction
     const size_t stage_budget = 192ull << 20;
     int chunk = static_cast<int>(std::max<size_t>(32, stage_budget / (sizeof(double) * sim_len * nvar) / 32 * 32));
@@ -974,6 +976,25 @@ double roadsurf_measure_fp64_tflops(int iterations)
     return -1.0;
   }
   return rs_measure_fp64(iterations > 0 ? iterations : 20000);
+}
+
+void roadsurf_release_workspace(void)
+{
+  // frees the pooled device and pinned buffers of every device (they are re-created on demand)
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  int current = 0;
+  cudaGetDevice(&current);
+  for (auto& kv : g_pool)
+    if (kv.second.p)
+    {
+      cudaSetDevice(kv.first.first);
+      cudaFree(kv.second.p);
+    }
+  g_pool.clear();
+  for (auto& kv : g_pinned_pool)
+    if (kv.second.p) cudaFreeHost(kv.second.p);
+  g_pinned_pool.clear();
+  cudaSetDevice(current);
 }
 
 int roadsurf_set_option(const char* name, int value)

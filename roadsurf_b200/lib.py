@@ -30,7 +30,8 @@ EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roa
            "roadsurf_run_host_soa", "roadsurf_read_input_derive",
            "roadsurf_last_batch_stats", "roadsurf_set_model", "roadsurf_run_device",
            "roadsurf_transpose_to_soa", "roadsurf_transpose_from_soa", "roadsurf_fill",
-           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_set_option", "roadsurf_last_launch",
+           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_set_option", "roadsurf_release_workspace",
+           "roadsurf_last_launch",
            "roadsurf_version")
 
 
@@ -345,3 +346,7 @@ def read_input_derive(arrays, settings, forecast_step, latest_obs_index=None):
                                              None if lat is None else lat.ctypes.data_as(abi.c_int_p), loc_ptrs,
                                              ok.ctypes.data_as(abi.c_int_p)))
     return ok
+
+
+def release_workspace():
+    load().roadsurf_release_workspace()

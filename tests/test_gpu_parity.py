@@ -434,6 +434,11 @@ def test_batches_larger_than_the_device_budget_are_split(rslib):
     assert np.array_equal(st0, st1)
     for k in arrays.out:
         assert np.array_equal(arrays.out[k], split.out[k]), k
+    # pooled work buffers can be released and are re-created on demand
+    rslib.release_workspace()
+    again = arrays.copy()
+    assert np.array_equal(rslib.run_batch(again, settings, params), st0)
+    assert np.array_equal(again.out["TsurfOut"], arrays.out["TsurfOut"])
 
 
 def test_multi_gpu_sharding_inside_the_library(rslib):
