@@ -254,7 +254,15 @@ enum
   RS_O_ICE,
   RS_O_DEPOSIT,
   RS_O_ICE2,
-  RS_O_NVAR = 6
+  RS_O_NVAR = 6,
+  /* Extended set (RsDeviceBatch.out_nvar == RS_O_NVAR_EXT): what example2 stores per output time
+   * besides the six model outputs (examples/example2/src/QueryDataTools.cpp:325-341): the air and
+   * dew point temperature INPUTS at that step and the dew point deficit Tsurf - Tdew
+   * (calc_difference, :285-296: -9999 when either operand is NaN or <= -9000). */
+  RS_O_TAIR = 6,
+  RS_O_TDEW,
+  RS_O_DEWDEFICIT,
+  RS_O_NVAR_EXT = 9
 };
 
 /* Everything a launch needs, as DEVICE pointers (on the current device).  `ld` is the padded
@@ -275,9 +283,11 @@ typedef struct RsDeviceBatch
   const int* time_fields;     /* [6][sim_len]: year, month, day, hour, minute, second */
   const double* local;        /* [RS_L_NLOCAL][ld] */
   const double* horizons;     /* [360][ld] local horizon angles, or NULL (all zero) */
-  double* out;                /* [RS_O_NVAR][n_out][ld] */
-  int out_stride;             /* write step i (1-based) when (i-1) % out_stride == 0 */
-  int n_out;                  /* ceil(sim_len / out_stride) */
+  double* out;                /* [out_nvar][n_out][ld] */
+  int out_stride;             /* write step i (1-based) when (i-1-out_start) is a non-negative
+                                 multiple of out_stride (get_write_stride,
+                                 examples/example2/src/QueryDataTools.cpp:270-284) */
+  int n_out;                  /* ceil((sim_len - out_start) / out_stride) */
   int* status;                /* [ld] status words (written) */
   double* state;              /* optional [RS_STATE_NPLANES(NLayers)][ld]: full per-point state, written
                                  at the end of every launch, read when step_begin > 1; or NULL */
@@ -295,7 +305,10 @@ typedef struct RsDeviceBatch
   int step_begin;
   int step_end;
   int forcing_step0;          /* forcing_mode 0: model step of forcing record 0 (0 -> 1) */
-  int out_slot0;              /* output slot (step-1)/out_stride stored at out[:, 0, :] */
+  int out_slot0;              /* output slot (step-1-out_start)/out_stride stored at out[:, 0, :] */
+  int out_start;              /* 0-based index of the first stored step (0 <= out_start < sim_len) */
+  int out_nvar;               /* 0 or RS_O_NVAR: the six model outputs; RS_O_NVAR_EXT: plus the
+                                 Tair / Tdew inputs and the dew point deficit */
 } RsDeviceBatch;
 
 enum

@@ -505,6 +505,8 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
       RsArgsCold ac;
       ac.state = nullptr;
       ac.counters = d_counters.as<unsigned long long>();
+      ac.out_start = 0;
+      ac.out_nvar = RS_O_NVAR;
       CU(cudaEventRecord(ev0, stream));
       CU(static_cast<cudaError_t>(
           rs_launch_run(&a, &ac, nl, opt_staging(), stream, &sh.launch.grid, &sh.launch.block,
@@ -736,6 +738,8 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     RsArgsCold ac;
     ac.state = nullptr;
     ac.counters = d_counters;
+    ac.out_start = 0;
+    ac.out_nvar = RS_O_NVAR;
     CU(static_cast<cudaError_t>(
         rs_launch_run(&a, &ac, nl, opt_staging(), st, &sh.launch.grid, &sh.launch.block, &sh.launch.regs_per_thread,
                       &sh.launch.smem_bytes)));
@@ -885,8 +889,14 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
     return fail(RS_ERR_BAD_ARGUMENT, "bad sim_len / out_stride / n_out");
   if (step_begin > step_end || step_end > b->sim_len || forcing_step0 > step_begin || b->out_slot0 < 0)
     return fail(RS_ERR_BAD_ARGUMENT, "bad step_begin / step_end / forcing_step0 / out_slot0");
+  if (b->out_start < 0 || b->out_start >= b->sim_len) return fail(RS_ERR_BAD_ARGUMENT, "out_start outside [0, sim_len)");
+  if (b->out_nvar != 0 && b->out_nvar != RS_O_NVAR && b->out_nvar != RS_O_NVAR_EXT)
+    return fail(RS_ERR_BAD_ARGUMENT, "out_nvar must be 0, RS_O_NVAR or RS_O_NVAR_EXT");
+  if (step_end - 1 >= b->out_start)
   {
-    const int first_slot = (step_begin - 1 + b->out_stride - 1) / b->out_stride, last_slot = (step_end - 1) / b->out_stride;
+    const int k0 = step_begin - 1 - b->out_start;
+    const int first_slot = k0 > 0 ? (k0 + b->out_stride - 1) / b->out_stride : 0;
+    const int last_slot = (step_end - 1 - b->out_start) / b->out_stride;
     if (last_slot >= first_slot && (first_slot < b->out_slot0 || last_slot - b->out_slot0 >= b->n_out))
       return fail(RS_ERR_BAD_ARGUMENT, "out tensor does not cover the output slots of [step_begin, step_end]");
   }
@@ -932,6 +942,8 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   RsArgsCold ac;
   ac.state = b->state;
   ac.counters = b->counters;
+  ac.out_start = b->out_start;
+  ac.out_nvar = b->out_nvar == RS_O_NVAR_EXT ? RS_O_NVAR_EXT : RS_O_NVAR;
   RsLaunchInfo li;
   std::memset(&li, 0, sizeof li);
   CU(static_cast<cudaError_t>(rs_launch_solar(b->time_fields, b->sim_len, b->solar, stream)));

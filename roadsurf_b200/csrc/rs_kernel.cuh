@@ -34,6 +34,8 @@ struct RsArgsCold
 {
   double* state;                 // [RS_STATE_NPLANES(N)][ld] or null
   unsigned long long* counters;  // [RS_CNT_N] or null
+  int out_start;                 // 0-based step index of output slot 0
+  int out_nvar;                  // RS_O_NVAR or RS_O_NVAR_EXT
 };
 
 // Host-callable launchers (rs_kernel.cu).  Return a cudaError_t as int.

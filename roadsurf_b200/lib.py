@@ -24,6 +24,8 @@ F_NAMES = ("tair", "tdew", "VZ", "Rhz", "prec", "SW", "LW", "SW_dir", "LW_net", 
  L_INIT_LEN, L_ACTIVE, L_NLOCAL) = range(11)
 O_NAMES = ("TsurfOut", "SnowOut", "WaterOut", "IceOut", "DepositOut", "Ice2Out")
 O_NVAR = 6
+O_NAMES_EXT = ("Tair", "Tdew", "DewPointDeficit")   # examples/example2/src/QueryDataTools.cpp:325-341
+O_NVAR_EXT = 9
 CNT_EXECUTED_STEPS, CNT_BL_ITERATIONS, CNT_COUPLING_PASSES, CNT_FAILED_POINTS, CNT_N = 0, 1, 2, 3, 8
 
 EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roadsurf_run_batch",
@@ -64,7 +66,8 @@ class RsDeviceBatch(C.Structure):
                 ("out_stride", C.c_int), ("n_out", C.c_int), ("status", C.c_void_p),
                 ("state", C.c_void_p), ("scratch", C.c_void_p), ("counters", C.c_void_p),
                 ("solar", C.c_void_p), ("step_begin", C.c_int), ("step_end", C.c_int),
-                ("forcing_step0", C.c_int), ("out_slot0", C.c_int)]
+                ("forcing_step0", C.c_int), ("out_slot0", C.c_int), ("out_start", C.c_int),
+                ("out_nvar", C.c_int)]
 
 
 class RsHostBatch(C.Structure):
@@ -208,7 +211,8 @@ class DeviceBatch:
     out [6, n_out, ld], status [ld]."""
 
     def __init__(self, npoints, sim_len, nlayers=15, n_records=None, nvar=F_NVAR, out_stride=1,
-                 coarse=False, horizons=False, coupling=False, state=False, device="cuda"):
+                 coarse=False, horizons=False, coupling=False, state=False, device="cuda",
+                 out_start=0, extended_outputs=False):
         import torch
         self.torch = torch
         self.npoints, self.sim_len, self.nlayers = int(npoints), int(sim_len), int(nlayers)
@@ -217,7 +221,9 @@ class DeviceBatch:
         self.n_records = int(n_records) if coarse else self.sim_len
         self.nvar = int(nvar)
         self.out_stride = int(out_stride)
-        self.n_out = (self.sim_len + self.out_stride - 1) // self.out_stride
+        self.out_start = int(out_start)
+        self.out_nvar = O_NVAR_EXT if extended_outputs else O_NVAR
+        self.n_out = (self.sim_len - self.out_start + self.out_stride - 1) // self.out_stride
         f64 = dict(dtype=torch.float64, device=device)
         self.forcing = torch.zeros((self.n_records, self.nvar, self.ld), **f64)
         self.record_step = torch.zeros(self.n_records, dtype=torch.int32, device=device) if coarse else None
@@ -229,7 +235,7 @@ class DeviceBatch:
         self.local[L_COUPLING_INDEX].fill_(-9999.0)
         self.local[L_TAIR_RELAX:L_RH_RELAX + 1].fill_(-9999.0)
         self.horizons = torch.zeros((360, self.ld), **f64) if horizons else None
-        self.out = torch.empty((O_NVAR, self.n_out, self.ld), **f64)
+        self.out = torch.empty((self.out_nvar, self.n_out, self.ld), **f64)
         self.status = torch.zeros(self.ld, dtype=torch.int32, device=device)
         self.state = torch.zeros((state_nplanes(nlayers), self.ld), **f64) if state else None
         self.scratch = torch.zeros((scratch_nplanes(nlayers), self.ld), **f64) if coupling else None
@@ -249,7 +255,8 @@ class DeviceBatch:
                              time_fields=ptr(self.time_fields), local=ptr(self.local),
                              horizons=ptr(self.horizons), out=ptr(out), out_stride=self.out_stride,
                              n_out=out.shape[1], status=ptr(self.status), state=ptr(self.state),
-                             scratch=ptr(self.scratch), counters=ptr(self.counters), solar=ptr(self.solar))
+                             scratch=ptr(self.scratch), counters=ptr(self.counters), solar=ptr(self.solar),
+                             out_start=self.out_start, out_nvar=self.out_nvar)
 
     def run(self, stream=None, **chunk):
         """Asynchronous launch on `stream` (a torch.cuda.Stream; default: the current stream).
@@ -305,7 +312,8 @@ class DeviceBatch:
     def outputs(self):
         """dict name -> numpy [npoints, n_out]."""
         o = self.out.cpu().numpy()
-        return {name: np.ascontiguousarray(o[v, :, :self.npoints].T) for v, name in enumerate(O_NAMES)}
+        names = O_NAMES + (O_NAMES_EXT if self.out_nvar == O_NVAR_EXT else ())
+        return {name: np.ascontiguousarray(o[v, :, :self.npoints].T) for v, name in enumerate(names)}
 
 
 def set_model(settings, params):

@@ -454,3 +454,55 @@ def test_multi_gpu_sharding_inside_the_library(rslib):
     assert np.array_equal(st0, st1)
     for k in arrays.out:
         assert np.array_equal(arrays.out[k], two.out[k]), k
+
+
+@pytest.mark.gpu
+def test_extended_output_set_with_start_offset(rslib, oracle):
+    """example2's stored set (examples/example2/src/QueryDataTools.cpp:270-341): outputs from a start
+    position at a stride, plus the Tair / Tdew inputs of those steps and the dew point deficit
+    Tsurf - Tdew (-9999 where either operand is missing).  One point fails its input check mid-run."""
+    import torch
+    npts, start, stride = 96, 37, 60
+    arrays, settings, params, _ = synth.make_case(npts, 6, seed=47, analysis_hours=3, use_coupling=1,
+                                                   use_relaxation=1, settings_kw=dict(coupling_minutes=60))
+    arrays.tair[5, 900] = 250.0          # CheckValues stops point 5 at step 901
+    arrays.tdew[7, start + 2 * stride] = -9999.9
+    ref = arrays.copy()
+    oracle.run_batch(ref, settings, params, nthreads=8)
+    rslib.set_model(settings, params)
+    sel = slice(start, None, stride)
+
+    def check(got):
+        assert np.array_equal(got["Tair"], arrays.tair[:, sel])
+        assert np.array_equal(got["Tdew"], arrays.tdew[:, sel])
+        ts, td = got["TsurfOut"], arrays.tdew[:, sel]
+        ok = (ts > -9000) & (td > -9000)
+        assert np.array_equal(got["DewPointDeficit"], np.where(ok, ts - td, -9999.0))
+        assert (got["DewPointDeficit"][5, 900 // stride + 1:] == -9999.0).all()
+        assert got["DewPointDeficit"][7, 2] == -9999.0
+        _assert_parity(compare({k: got[k] for k in ref.out}, {k: v[:, sel] for k, v in ref.out.items()}),
+                       max_mismatch=0.1)
+
+    db = rslib.DeviceBatch(npts, arrays.sim_len, horizons=True, coupling=True, state=True, out_stride=stride,
+                           out_start=start, extended_outputs=True)
+    db.load_point_arrays(arrays)
+    db.out.fill_(3.0)
+    db.run()
+    torch.cuda.synchronize()
+    assert db.out.shape[0] == rslib.O_NVAR_EXT and db.n_out == len(range(start, arrays.sim_len, stride))
+    check(db.outputs())
+
+    # the same in two time chunks, each with a chunk-local output tensor
+    want = db.out.clone()
+    cend = arrays.local[0].couplingIndexI
+    cut = cend + 100                                    # chunk 1 = steps [1, cut], chunk 2 the rest
+    slots1 = len(range(start, cut, stride))             # 0-based steps start, start+stride, ... < cut
+    ch = rslib.DeviceBatch(npts, arrays.sim_len, horizons=True, coupling=True, state=True, out_stride=stride,
+                           out_start=start, extended_outputs=True)
+    ch.load_point_arrays(arrays)
+    o1 = torch.full((rslib.O_NVAR_EXT, slots1, ch.ld), 5.0, dtype=torch.float64, device="cuda")
+    o2 = torch.full((rslib.O_NVAR_EXT, db.n_out - slots1, ch.ld), 5.0, dtype=torch.float64, device="cuda")
+    ch.run(step_begin=1, step_end=cut, out=o1, out_slot0=0)
+    ch.run(step_begin=cut + 1, step_end=arrays.sim_len, out=o2, out_slot0=slots1)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([o1, o2], dim=1), want)
