@@ -309,6 +309,13 @@ typedef struct RsDeviceBatch
   int out_start;              /* 0-based index of the first stored step (0 <= out_start < sim_len) */
   int out_nvar;               /* 0 or RS_O_NVAR: the six model outputs; RS_O_NVAR_EXT: plus the
                                  Tair / Tdew inputs and the dew point deficit */
+  int coupling_window_end;    /* 0, or the caller's assertion that every coupled point of the batch has
+                                 couplingIndexI == this value (points that do not are flagged
+                                 RS_ST_BAD_WINDOW).  With `state` and `scratch` present it enables lane
+                                 compaction between coupling iterations: the run is split at the
+                                 window end and only the points that want another iteration are
+                                 re-run, in dense warps (option "coupling_compaction_passes").
+                                 Results are bit-identical to the single launch. */
 } RsDeviceBatch;
 
 enum
@@ -323,8 +330,9 @@ enum
 /* Number of fp64 planes of the per-point state for a given NLayers: Tmp(0:N+1), 10 surface scalars,
  * 3 relaxation latches, 5 radiation-coupling scalars, 1 flag word. */
 #define RS_STATE_NPLANES(nlayers) ((nlayers) + 2 + 19)
-/* Number of fp64 planes of the coupling work space (window snapshot + bracket scalars). */
-#define RS_SCRATCH_NPLANES(nlayers) (2 * (nlayers) + 16)
+/* Number of fp64 planes of the coupling work space (window snapshot, bracket scalars, one plane for
+ * the compaction index list). */
+#define RS_SCRATCH_NPLANES(nlayers) (2 * (nlayers) + 17)
 
 /* Upload settings + parameters for subsequent roadsurf_run_device calls on the current device
  * (derives layer geometry, conductivities and log terms: src/Initialization.f90:181-358,
@@ -388,6 +396,9 @@ void roadsurf_release_workspace(void);
  * through a ring of shared-memory tiles filled by TMA bulk copies a few steps ahead, 0 = direct
  * coalesced read-only loads (default; measured 3-6 % faster on B200).  The default can
  * also be set with the environment variable ROADSURF_B200_FORCING_STAGING=1.  Results are identical.
+ * "coupling_compaction_passes" (default 6, 0 = off): with RsDeviceBatch.coupling_window_end set, the
+ * number of compacted passes over the coupling window before the points still iterating finish
+ * inside the last launch.
  * "max_points_per_device_batch": cap on the points roadsurf_run_batch puts into one device batch
  * (0 = bounded by free device memory only); batches beyond it are processed one after another. */
 int roadsurf_set_option(const char* name, int value);

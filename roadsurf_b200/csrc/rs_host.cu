@@ -35,6 +35,10 @@ std::atomic<int> g_launches_total{0};
 // per-warp TMA ring in shared memory, 0 = direct read-only loads (default: measured faster).
 std::atomic<int> g_opt_staging{-1};
 std::atomic<int> g_opt_max_slots{0};  // test hook: cap on points per device batch in roadsurf_run_batch (0 = memory bound)
+// coupling_compaction_passes: number of compacted passes over the coupling window before the points
+// still iterating are left to finish inside the last launch (0 = one launch, warps repeat in place).
+std::atomic<int> g_opt_compaction{6};
+int opt_compaction_passes() { return g_opt_compaction.load(); }
 int opt_staging()
 {
   int v = g_opt_staging.load();
@@ -503,7 +507,7 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
       a.status = d_status.as<int>();
       a.scratch = model.use_coupling ? d_scratch.as<double>() : nullptr;
       RsArgsCold ac;
-      ac.state = nullptr;
+      std::memset(&ac, 0, sizeof ac);
       ac.counters = d_counters.as<unsigned long long>();
       ac.out_start = 0;
       ac.out_nvar = RS_O_NVAR;
@@ -736,7 +740,7 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     a.status = d_status[s];
     a.scratch = d_scratch[s];
     RsArgsCold ac;
-    ac.state = nullptr;
+    std::memset(&ac, 0, sizeof ac);
     ac.counters = d_counters;
     ac.out_start = 0;
     ac.out_nvar = RS_O_NVAR;
@@ -940,6 +944,7 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   a.status = b->status;
   a.scratch = b->scratch;
   RsArgsCold ac;
+  std::memset(&ac, 0, sizeof ac);
   ac.state = b->state;
   ac.counters = b->counters;
   ac.out_start = b->out_start;
@@ -948,8 +953,56 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   std::memset(&li, 0, sizeof li);
   CU(static_cast<cudaError_t>(rs_launch_solar(b->time_fields, b->sim_len, b->solar, stream)));
   ++g_launches_total;
-  CU(static_cast<cudaError_t>(rs_launch_run(&a, &ac, m.nlayers, opt_staging(), stream, &li.grid, &li.block,
-                                            &li.regs_per_thread, &li.smem_bytes)));
+
+  // ---- coupling with lane compaction.  A warp repeats the coupling window until its slowest lane
+  // has converged; when the caller asserts one common window, the run is split at the window end
+  // instead: [step_begin, end] for everyone, then passes over a compacted list of the points that
+  // want another iteration (state through the SoA planes), then [end + 1, step_end] with the few
+  // points still iterating gathered in warps of their own.  Same arithmetic per point, bit-identical
+  // results; all launches are queued on `stream` without a host synchronisation.
+  const int wend = b->coupling_window_end;
+  const int passes = opt_compaction_passes();
+  if (m.use_coupling && wend > 0 && passes > 0 && b->state && b->scratch && !opt_staging() && forcing_step0 == 1 &&
+      step_begin <= 1 && wend + 1 < step_end)
+  {
+    int* index = reinterpret_cast<int*>(b->scratch + static_cast<size_t>(2 * m.nlayers + 16) * b->ld);
+    int* n_index = index + b->ld;
+    const double* flags = b->state + static_cast<size_t>(m.nlayers + 2 + 18) * b->ld;
+    RsArgs a1 = a;
+    RsArgsCold c1 = ac;
+    a1.step_end = wend;
+    c1.mode = RS_MODE_SPLIT;
+    c1.window_end = wend;
+    CU(static_cast<cudaError_t>(rs_launch_run(&a1, &c1, m.nlayers, 0, stream, &li.grid, &li.block,
+                                              &li.regs_per_thread, &li.smem_bytes)));
+    ++g_launches_total;
+    RsArgs a2 = a;
+    RsArgsCold c2 = c1;
+    a2.step_begin = wend + 1;
+    a2.step_end = wend;
+    c2.mode = RS_MODE_SPLIT | RS_MODE_ONE_PASS;
+    c2.index = index;
+    c2.n_index = n_index;
+    for (int k = 0; k < passes; ++k)
+    {
+      CU(static_cast<cudaError_t>(rs_launch_partition(flags, b->ld, b->npoints, 0, index, n_index, stream)));
+      CU(static_cast<cudaError_t>(rs_launch_run(&a2, &c2, m.nlayers, 0, stream, &li.grid, &li.block,
+                                                &li.regs_per_thread, &li.smem_bytes)));
+      g_launches_total += 2;
+    }
+    CU(static_cast<cudaError_t>(rs_launch_partition(flags, b->ld, b->npoints, 1, index, n_index, stream)));
+    ++g_launches_total;
+    RsArgs a3 = a;
+    RsArgsCold c3 = c1;
+    a3.step_begin = wend + 1;
+    c3.index = index;
+    c3.n_index = n_index;
+    CU(static_cast<cudaError_t>(rs_launch_run(&a3, &c3, m.nlayers, 0, stream, &li.grid, &li.block,
+                                              &li.regs_per_thread, &li.smem_bytes)));
+  }
+  else
+    CU(static_cast<cudaError_t>(rs_launch_run(&a, &ac, m.nlayers, opt_staging(), stream, &li.grid, &li.block,
+                                              &li.regs_per_thread, &li.smem_bytes)));
   li.nlayers = m.nlayers;
   li.forcing_mode = b->forcing_mode;
   li.launches_total = ++g_launches_total;
@@ -1014,6 +1067,11 @@ int roadsurf_set_option(const char* name, int value)
   if (name && std::strcmp(name, "forcing_staging") == 0)
   {
     g_opt_staging = value ? 1 : 0;
+    return RS_OK;
+  }
+  if (name && std::strcmp(name, "coupling_compaction_passes") == 0)
+  {
+    g_opt_compaction = value > 0 ? (value > 30 ? 30 : value) : 0;
     return RS_OK;
   }
   if (name && std::strcmp(name, "max_points_per_device_batch") == 0)

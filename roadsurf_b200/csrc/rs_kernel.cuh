@@ -36,11 +36,26 @@ struct RsArgsCold
   unsigned long long* counters;  // [RS_CNT_N] or null
   int out_start;                 // 0-based step index of output slot 0
   int out_nvar;                  // RS_O_NVAR or RS_O_NVAR_EXT
+  // Lane compaction between coupling passes (see rs_launch_run_coupled): thread t handles point
+  // index[t] for t < *n_index (threads beyond are ghosts that write nothing); null = thread t is point t.
+  const int* index;
+  const int* n_index;
+  int mode;                      // RS_MODE_* bits
+  int window_end;                // RS_MODE_SPLIT: the coupling window end every coupled point must have
+};
+
+enum
+{
+  RS_MODE_SPLIT = 1,     // the launch may begin / end at the end of the coupling window (state carries
+                         // the iteration), and rewinds may go before step_begin
+  RS_MODE_ONE_PASS = 2   // enter at the restart decision of step window_end + 1, re-run the window
+                         // once and stop after step window_end (state written)
 };
 
 // Host-callable launchers (rs_kernel.cu).  Return a cudaError_t as int.
 int rs_upload_model(const RsModel* m);
 int rs_launch_solar(const int* tf, int sim_len, double* table, void* stream);
+int rs_launch_partition(const double* flags_plane, int ld, int npoints, int sorted, int* index, int* n_index, void* stream);
 int rs_launch_run(const RsArgs* a, const RsArgsCold* cold, int nlayers, int staged, void* stream, int* grid, int* block, int* regs,
                   int* smem);
 int rs_launch_transpose_to_soa(const double* src, long long src_ld, int npoints, int n, double* dst,

@@ -42,7 +42,7 @@ def state_nplanes(nlayers):
 
 
 def scratch_nplanes(nlayers):
-    return 2 * nlayers + 16
+    return 2 * nlayers + 17
 
 
 class RsBatchStats(C.Structure):
@@ -67,7 +67,7 @@ class RsDeviceBatch(C.Structure):
                 ("state", C.c_void_p), ("scratch", C.c_void_p), ("counters", C.c_void_p),
                 ("solar", C.c_void_p), ("step_begin", C.c_int), ("step_end", C.c_int),
                 ("forcing_step0", C.c_int), ("out_slot0", C.c_int), ("out_start", C.c_int),
-                ("out_nvar", C.c_int)]
+                ("out_nvar", C.c_int), ("coupling_window_end", C.c_int)]
 
 
 class RsHostBatch(C.Structure):
@@ -223,6 +223,7 @@ class DeviceBatch:
         self.out_stride = int(out_stride)
         self.out_start = int(out_start)
         self.out_nvar = O_NVAR_EXT if extended_outputs else O_NVAR
+        self.coupling_window_end = 0    # set by load_local when all coupled points share one window
         self.n_out = (self.sim_len - self.out_start + self.out_stride - 1) // self.out_stride
         f64 = dict(dtype=torch.float64, device=device)
         self.forcing = torch.zeros((self.n_records, self.nvar, self.ld), **f64)
@@ -256,7 +257,8 @@ class DeviceBatch:
                              horizons=ptr(self.horizons), out=ptr(out), out_stride=self.out_stride,
                              n_out=out.shape[1], status=ptr(self.status), state=ptr(self.state),
                              scratch=ptr(self.scratch), counters=ptr(self.counters), solar=ptr(self.solar),
-                             out_start=self.out_start, out_nvar=self.out_nvar)
+                             out_start=self.out_start, out_nvar=self.out_nvar,
+                             coupling_window_end=self.coupling_window_end if (step_begin, step_end) == (0, 0) else 0)
 
     def run(self, stream=None, **chunk):
         """Asynchronous launch on `stream` (a torch.cuda.Stream; default: the current stream).
@@ -291,6 +293,11 @@ class DeviceBatch:
             L[:, p] = (lp.tair_relax, lp.VZ_relax, lp.RH_relax, lp.couplingTsurf, lp.lat, lp.lon,
                        lp.sky_view, lp.couplingIndexI, lp.InitLenI, 1.0)
         self.local.copy_(torch.from_numpy(L))
+        # one common coupling window (the usual case: one analysis time for the whole batch) lets the
+        # library compact lanes between coupling iterations
+        coupled = (L[L_COUPLING_TSURF, :n] >= -100) & (L[L_COUPLING_INDEX, :n] >= 1)
+        ends = np.unique(L[L_COUPLING_INDEX, :n][coupled])
+        self.coupling_window_end = int(ends[0]) if (ends.size == 1 and self.state is not None) else 0
         if self.horizons is not None and horizons is not None:
             H = np.zeros((360, self.ld))
             H[:, :n] = np.asarray(horizons).T

@@ -8,8 +8,10 @@ P = int(os.environ.get("RS_POINTS", 100000)); base = 2048
 CPL = int(os.environ.get("RS_COUPLING", 1)); RLX = int(os.environ.get("RS_RELAX", 1))
 arrays, settings, params, rec = synth.make_case(base, 48, seed=20191205, analysis_hours=6, use_coupling=CPL, use_relaxation=RLX)
 lib.set_model(settings, params)
-small = lib.DeviceBatch(base, arrays.sim_len, horizons=True, coupling=bool(CPL)); small.load_point_arrays(arrays)
-db = lib.DeviceBatch(P, arrays.sim_len, horizons=True, coupling=bool(CPL))
+small = lib.DeviceBatch(base, arrays.sim_len, horizons=True, coupling=bool(CPL), state=True); small.load_point_arrays(arrays)
+db = lib.DeviceBatch(P, arrays.sim_len, horizons=True, coupling=bool(CPL), state=True)
+if "RS_COMPACT" in os.environ: lib.set_option("coupling_compaction_passes", int(os.environ["RS_COMPACT"]))
+db.coupling_window_end = small.coupling_window_end
 for t0 in range(0, arrays.sim_len, 256):   # tile in time slices to bound temporaries
     t1 = min(arrays.sim_len, t0 + 256)
     db.forcing[t0:t1] = small.forcing[t0:t1].repeat(1, 1, (db.ld + base - 1) // base)[:, :, :db.ld]
@@ -25,7 +27,7 @@ for _ in range(2):
     e0.record(); db.run(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 cnt = db.counters.cpu().numpy(); st = db.status[:P].cpu().numpy()
 ms = min(ts); nominal = P * arrays.sim_len
-print(json.dumps({"config": "c3", "coupling": CPL, "relaxation": RLX, "points": P, "sim_len": arrays.sim_len, "kernel_ms": round(ms, 1),
+print(json.dumps({"config": "c3", "coupling": CPL, "relaxation": RLX, "compaction_passes": os.environ.get("RS_COMPACT", "default"), "window_end": db.coupling_window_end, "points": P, "sim_len": arrays.sim_len, "kernel_ms": round(ms, 1),
                   "point_steps_per_s_nominal": nominal / ms * 1e3, "executed_over_nominal": float(cnt[0]) / nominal,
                   "coupling_passes_per_warp": float(cnt[2]) / (db.ld / 32), "coupling_failed_fraction": float(((st & 16) > 0).mean()),
                   "algorithmic_GBps": nominal * 136 / ms / 1e6, "launch": lib.last_launch()}))

@@ -506,3 +506,61 @@ def test_extended_output_set_with_start_offset(rslib, oracle):
     ch.run(step_begin=cut + 1, step_end=arrays.sim_len, out=o2, out_slot0=slots1)
     torch.cuda.synchronize()
     assert torch.equal(torch.cat([o1, o2], dim=1), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("passes", [1, 3, 30])
+def test_coupling_lane_compaction_is_bit_identical(rslib, passes):
+    """The run split at the coupling window end, with compacted passes over the points that want
+    another iteration and the stragglers finishing inside the last launch, against the single
+    launch in which whole warps repeat the window: outputs, status words, per-point state and the
+    number of executed point-steps are identical.  Includes points without coupling, a point that
+    fails its input check inside the window and one that fails right after it."""
+    import torch
+    npts = 777
+    arrays, settings, params, _ = synth.make_case(npts, 5, seed=51, analysis_hours=4, use_coupling=1,
+                                                   use_relaxation=1, settings_kw=dict(coupling_minutes=90))
+    cend = arrays.local[0].couplingIndexI
+    for p in (3, 40, 41):                      # uncoupled points among coupled ones
+        arrays.local[p].couplingTsurf = -9999.9
+        arrays.local[p].couplingIndexI = -9999
+    arrays.tair[10, cend - 50] = 250.0         # fails inside the window (0-based index = step - 1)
+    arrays.tair[11, cend] = 250.0              # fails CheckValues(window end + 1)
+    arrays.tair[12, cend + 30] = 250.0         # fails later
+    rslib.set_model(settings, params)
+
+    def run(compaction):
+        db = rslib.DeviceBatch(npts, arrays.sim_len, horizons=True, coupling=True, state=True)
+        db.load_point_arrays(arrays)
+        assert db.coupling_window_end == cend
+        if not compaction:
+            db.coupling_window_end = 0
+        db.out.fill_(9.0)
+        db.run()
+        torch.cuda.synchronize()
+        return db
+
+    rslib.set_option("coupling_compaction_passes", passes)
+    try:
+        got = run(True)
+        launches = rslib.last_launch()["launches_total"]
+    finally:
+        rslib.set_option("coupling_compaction_passes", 6)
+    want = run(False)
+    assert rslib.last_launch()["launches_total"] - launches == 2      # solar table + one run kernel
+    assert torch.equal(got.out, want.out)
+    assert torch.equal(got.status, want.status)
+    assert torch.equal(got.state[:, :npts], want.state[:, :npts])
+    assert int(got.counters[rslib.CNT_EXECUTED_STEPS]) == int(want.counters[rslib.CNT_EXECUTED_STEPS])
+    assert int(got.counters[rslib.CNT_FAILED_POINTS]) == int(want.counters[rslib.CNT_FAILED_POINTS]) == 3
+    st = want.status[:npts].cpu().numpy()
+    assert (st & rslib.ST_COUPLING_USED).astype(bool).sum() == npts - 3
+
+    # a point whose window differs from the asserted one is refused, not silently mis-run
+    bad = rslib.DeviceBatch(npts, arrays.sim_len, horizons=True, coupling=True, state=True)
+    bad.load_point_arrays(arrays)
+    bad.local[rslib.L_COUPLING_INDEX, 5] = cend - 7
+    bad.run()
+    torch.cuda.synchronize()
+    st = bad.status[:npts].cpu().numpy()
+    assert st[5] & rslib.ST_BAD_WINDOW and not (np.delete(st, 5) & rslib.ST_BAD_WINDOW).any()
