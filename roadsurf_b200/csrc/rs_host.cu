@@ -963,7 +963,7 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   const int wend = b->coupling_window_end;
   const int passes = opt_compaction_passes();
   if (m.use_coupling && wend > 0 && passes > 0 && b->state && b->scratch && !opt_staging() && forcing_step0 == 1 &&
-      step_begin <= 1 && wend + 1 < step_end)
+      b->forcing_mode == 0 && step_begin <= 1 && wend + 1 < step_end)
   {
     int* index = reinterpret_cast<int*>(b->scratch + static_cast<size_t>(2 * m.nlayers + 16) * b->ld);
     int* n_index = index + b->ld;
