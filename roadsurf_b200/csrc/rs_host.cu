@@ -65,6 +65,62 @@ int fail(int code, const std::string& msg)
       return fail(RS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                 \
   } while (0)
 
+// One model run on `stream`: a single launch of the step kernel, or -- coupling with lane compaction --
+// several.  A warp repeats the coupling window until its slowest lane has converged; when every
+// coupled point of the batch has the same window end `wend` (> 0) and the state planes are there,
+// the run is split at the window end instead: [step_begin, wend] for everyone, then passes over a
+// compacted list of the points that want another iteration (state through the SoA planes), then
+// [wend + 1, step_end] with the few points still iterating gathered in warps of their own.  Same
+// arithmetic per point, bit-identical results; all launches are queued without a host
+// synchronisation.  *launches receives the number of kernels queued.
+int launch_model(const RsArgs& a, const RsArgsCold& ac, const RsModel& m, int wend, void* stream, RsLaunchInfo* li,
+                 int* launches)
+{
+  const int passes = opt_compaction_passes();
+  *launches = 0;
+  if (!(m.use_coupling && wend > 0 && passes > 0 && ac.state && a.scratch && !opt_staging() && a.forcing_step0 == 1 &&
+        a.forcing_mode == 0 && a.step_begin <= 1 && wend + 1 < a.step_end))
+  {
+    CU(static_cast<cudaError_t>(rs_launch_run(&a, &ac, m.nlayers, opt_staging(), stream, &li->grid, &li->block,
+                                              &li->regs_per_thread, &li->smem_bytes)));
+    *launches = 1;
+    return RS_OK;
+  }
+  int* index = reinterpret_cast<int*>(a.scratch + static_cast<size_t>(2 * m.nlayers + 16) * a.ld);
+  int* n_index = index + a.ld;
+  const double* flags = ac.state + static_cast<size_t>(m.nlayers + 2 + 18) * a.ld;
+  RsArgs a1 = a;
+  RsArgsCold c1 = ac;
+  a1.step_end = wend;
+  c1.mode = RS_MODE_SPLIT;
+  c1.window_end = wend;
+  CU(static_cast<cudaError_t>(rs_launch_run(&a1, &c1, m.nlayers, 0, stream, &li->grid, &li->block,
+                                            &li->regs_per_thread, &li->smem_bytes)));
+  RsArgs a2 = a;
+  RsArgsCold c2 = c1;
+  a2.step_begin = wend + 1;
+  a2.step_end = wend;
+  c2.mode = RS_MODE_SPLIT | RS_MODE_ONE_PASS;
+  c2.index = index;
+  c2.n_index = n_index;
+  for (int k = 0; k < passes; ++k)
+  {
+    CU(static_cast<cudaError_t>(rs_launch_partition(flags, a.ld, a.npoints, 0, index, n_index, stream)));
+    CU(static_cast<cudaError_t>(rs_launch_run(&a2, &c2, m.nlayers, 0, stream, &li->grid, &li->block,
+                                              &li->regs_per_thread, &li->smem_bytes)));
+  }
+  CU(static_cast<cudaError_t>(rs_launch_partition(flags, a.ld, a.npoints, 1, index, n_index, stream)));
+  RsArgs a3 = a;
+  RsArgsCold c3 = c1;
+  a3.step_begin = wend + 1;
+  c3.index = index;
+  c3.n_index = n_index;
+  CU(static_cast<cudaError_t>(rs_launch_run(&a3, &c3, m.nlayers, 0, stream, &li->grid, &li->block,
+                                            &li->regs_per_thread, &li->smem_bytes)));
+  *launches = 2 * passes + 3;
+  return RS_OK;
+}
+
 double now_ms()
 {
   using namespace std::chrono;
@@ -291,6 +347,19 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
     while (loose_pos < loose.size()) slots.push_back(loose[loose_pos++]);
     while (slots.size() % 32 != 0) slots.push_back(-1);
     ++sh.stats.groups;
+    // one coupling window in the whole group (the usual case: one analysis time): lane compaction
+    // between coupling iterations (launch_model); needs the per-point state planes
+    int wend = 0;
+    {
+      int nwin = 0;
+      for (auto& kv : by_window)
+        if (kv.first != -1)
+        {
+          ++nwin;
+          wend = static_cast<int>(kv.first);
+        }
+      if (nwin != 1 || opt_compaction_passes() < 1) wend = 0;
+    }
 
     std::atomic<bool> any_depth_a(false), any_sky_a(false);
     parallel_for(static_cast<int>(g.points.size()), host_threads(), [&](int k) {
@@ -313,7 +382,8 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
 
     // ---- device batches that fit the memory budget -------------------------------------------
     const size_t per_slot = sizeof(double) * (static_cast<size_t>(sim_len) * (nvar + RS_O_NVAR) + RS_L_NLOCAL +
-                                              (any_sky ? 360 : 0) + RS_SCRATCH_NPLANES(nl)) + sizeof(int);
+                                              (any_sky ? 360 : 0) + RS_SCRATCH_NPLANES(nl) +
+                                              (wend > 0 ? RS_STATE_NPLANES(nl) : 0)) + sizeof(int);
     size_t budget = static_cast<size_t>(free_b * 0.80);
     size_t max_slots = budget / per_slot / 32 * 32;
     if (max_slots < 32) return fail(RS_ERR_CUDA, "not enough device memory for one warp of points");
@@ -341,7 +411,7 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
     {
       const int ld = static_cast<int>(std::min(max_slots, slots.size() - s0));
       chunk = std::min(chunk, ld);
-      PooledDevice d_forcing, d_out, d_local, d_hor, d_status, d_scratch, d_stage, d_stage2, d_counters;
+      PooledDevice d_forcing, d_out, d_local, d_hor, d_status, d_scratch, d_stage, d_stage2, d_counters, d_state;
       const int dv = sh.device;
       CU(d_forcing.alloc(dv, 200, sizeof(double) * sim_len * nvar * ld));
       CU(d_out.alloc(dv, 201, sizeof(double) * RS_O_NVAR * sim_len * ld));
@@ -349,6 +419,7 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
       if (any_sky) CU(d_hor.alloc(dv, 203, sizeof(double) * 360 * ld));
       CU(d_status.alloc(dv, 204, sizeof(int) * ld));
       if (model.use_coupling) CU(d_scratch.alloc(dv, 205, sizeof(double) * RS_SCRATCH_NPLANES(nl) * ld));
+      if (wend > 0) CU(d_state.alloc(dv, 211, sizeof(double) * RS_STATE_NPLANES(nl) * ld));
       const size_t stage_bytes = sizeof(double) * static_cast<size_t>(chunk) * sim_len * std::max(nvar, (int)RS_O_NVAR);
       CU(d_stage.alloc(dv, 206, stage_bytes));
       CU(d_stage2.alloc(dv, 207, stage_bytes));
@@ -511,12 +582,15 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
       ac.counters = d_counters.as<unsigned long long>();
       ac.out_start = 0;
       ac.out_nvar = RS_O_NVAR;
+      ac.state = wend > 0 ? d_state.as<double>() : nullptr;
       CU(cudaEventRecord(ev0, stream));
-      CU(static_cast<cudaError_t>(
-          rs_launch_run(&a, &ac, nl, opt_staging(), stream, &sh.launch.grid, &sh.launch.block,
-                        &sh.launch.regs_per_thread, &sh.launch.smem_bytes)));
+      {
+        int n = 0;
+        const int rc = launch_model(a, ac, model, wend, stream, &sh.launch, &n);
+        if (rc != RS_OK) return rc;
+        sh.stats.kernel_launches += n;
+      }
       CU(cudaEventRecord(ev1, stream));
-      ++sh.stats.kernel_launches;
       sh.launch.nlayers = nl;
       sh.launch.forcing_mode = 0;
       CU(cudaStreamSynchronize(stream));
@@ -954,55 +1028,12 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   CU(static_cast<cudaError_t>(rs_launch_solar(b->time_fields, b->sim_len, b->solar, stream)));
   ++g_launches_total;
 
-  // ---- coupling with lane compaction.  A warp repeats the coupling window until its slowest lane
-  // has converged; when the caller asserts one common window, the run is split at the window end
-  // instead: [step_begin, end] for everyone, then passes over a compacted list of the points that
-  // want another iteration (state through the SoA planes), then [end + 1, step_end] with the few
-  // points still iterating gathered in warps of their own.  Same arithmetic per point, bit-identical
-  // results; all launches are queued on `stream` without a host synchronisation.
-  const int wend = b->coupling_window_end;
-  const int passes = opt_compaction_passes();
-  if (m.use_coupling && wend > 0 && passes > 0 && b->state && b->scratch && !opt_staging() && forcing_step0 == 1 &&
-      b->forcing_mode == 0 && step_begin <= 1 && wend + 1 < step_end)
   {
-    int* index = reinterpret_cast<int*>(b->scratch + static_cast<size_t>(2 * m.nlayers + 16) * b->ld);
-    int* n_index = index + b->ld;
-    const double* flags = b->state + static_cast<size_t>(m.nlayers + 2 + 18) * b->ld;
-    RsArgs a1 = a;
-    RsArgsCold c1 = ac;
-    a1.step_end = wend;
-    c1.mode = RS_MODE_SPLIT;
-    c1.window_end = wend;
-    CU(static_cast<cudaError_t>(rs_launch_run(&a1, &c1, m.nlayers, 0, stream, &li.grid, &li.block,
-                                              &li.regs_per_thread, &li.smem_bytes)));
-    ++g_launches_total;
-    RsArgs a2 = a;
-    RsArgsCold c2 = c1;
-    a2.step_begin = wend + 1;
-    a2.step_end = wend;
-    c2.mode = RS_MODE_SPLIT | RS_MODE_ONE_PASS;
-    c2.index = index;
-    c2.n_index = n_index;
-    for (int k = 0; k < passes; ++k)
-    {
-      CU(static_cast<cudaError_t>(rs_launch_partition(flags, b->ld, b->npoints, 0, index, n_index, stream)));
-      CU(static_cast<cudaError_t>(rs_launch_run(&a2, &c2, m.nlayers, 0, stream, &li.grid, &li.block,
-                                                &li.regs_per_thread, &li.smem_bytes)));
-      g_launches_total += 2;
-    }
-    CU(static_cast<cudaError_t>(rs_launch_partition(flags, b->ld, b->npoints, 1, index, n_index, stream)));
-    ++g_launches_total;
-    RsArgs a3 = a;
-    RsArgsCold c3 = c1;
-    a3.step_begin = wend + 1;
-    c3.index = index;
-    c3.n_index = n_index;
-    CU(static_cast<cudaError_t>(rs_launch_run(&a3, &c3, m.nlayers, 0, stream, &li.grid, &li.block,
-                                              &li.regs_per_thread, &li.smem_bytes)));
+    int n = 0;
+    const int rc = launch_model(a, ac, m, b->coupling_window_end, stream, &li, &n);
+    if (rc != RS_OK) return rc;
+    g_launches_total += n - 1;  // (the last one is counted below)
   }
-  else
-    CU(static_cast<cudaError_t>(rs_launch_run(&a, &ac, m.nlayers, opt_staging(), stream, &li.grid, &li.block,
-                                              &li.regs_per_thread, &li.smem_bytes)));
   li.nlayers = m.nlayers;
   li.forcing_mode = b->forcing_mode;
   li.launches_total = ++g_launches_total;
