@@ -564,3 +564,37 @@ def test_coupling_lane_compaction_is_bit_identical(rslib, passes):
     torch.cuda.synchronize()
     st = bad.status[:npts].cpu().numpy()
     assert st[5] & rslib.ST_BAD_WINDOW and not (np.delete(st, 5) & rslib.ST_BAD_WINDOW).any()
+
+
+@pytest.mark.gpu
+def test_replicated_coupled_points_agree_anywhere_in_a_large_batch(rslib):
+    """Config-3-like property test at a size where the compacted passes span many warps: 1536 distinct
+    coupled points tiled to 30 000 (plus a ragged tail).  Every replica, wherever the compaction put
+    it in any pass, must reproduce the result of the small single-launch run bit for bit."""
+    import torch
+    base, P = 1536, 30_011
+    arrays, settings, params, _ = synth.make_case(base, 8, seed=61, analysis_hours=4, use_coupling=1,
+                                                   use_relaxation=1)
+    rslib.set_model(settings, params)
+    small = rslib.DeviceBatch(base, arrays.sim_len, horizons=True, coupling=True)   # no state: one launch
+    small.load_point_arrays(arrays)
+    small.run()
+    big = rslib.DeviceBatch(P, arrays.sim_len, horizons=True, coupling=True, state=True)
+    idx = torch.arange(big.ld, device="cuda") % base
+    for t0 in range(0, arrays.sim_len, 512):
+        big.forcing[t0:t0 + 512] = small.forcing[t0:t0 + 512][:, :, idx]
+    big.time_fields.copy_(small.time_fields)
+    big.local.copy_(small.local[:, idx])
+    big.local[rslib.L_ACTIVE, P:] = 0
+    big.horizons.copy_(small.horizons[:, idx])
+    big.coupling_window_end = arrays.local[0].couplingIndexI
+    big.run()
+    torch.cuda.synchronize()
+    assert rslib.last_launch()["launches_total"] > 0
+    assert torch.equal(big.out[:, :, :P], small.out[:, :, idx[:P]])
+    assert torch.equal(big.status[:P], small.status[idx[:P]])
+    passes_small = int(small.counters[rslib.CNT_COUPLING_PASSES]) / (small.ld / 32)
+    passes_big = int(big.counters[rslib.CNT_COUPLING_PASSES]) / (big.ld / 32)
+    assert passes_big < 0.6 * passes_small, (passes_big, passes_small)   # the compaction did compact
+    assert int(big.counters[rslib.CNT_EXECUTED_STEPS]) * base == pytest.approx(
+        int(small.counters[rslib.CNT_EXECUTED_STEPS]) * P, rel=0.02)
