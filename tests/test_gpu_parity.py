@@ -434,6 +434,24 @@ def test_batches_larger_than_the_device_budget_are_split(rslib):
     assert np.array_equal(st0, st1)
     for k in arrays.out:
         assert np.array_equal(arrays.out[k], split.out[k]), k
+    # one common window: every device batch runs the compacted coupling passes on its own state planes
+    uni, settings_u, params_u, _ = synth.make_case(300, 4, seed=48, analysis_hours=4, use_coupling=1,
+                                                    use_relaxation=1, settings_kw=dict(coupling_minutes=120))
+    uni_split, uni_single = uni.copy(), uni.copy()
+    st_u = rslib.run_batch(uni, settings_u, params_u)
+    try:
+        rslib.set_option("max_points_per_device_batch", 96)
+        st_us = rslib.run_batch(uni_split, settings_u, params_u)
+        rslib.set_option("max_points_per_device_batch", 0)
+        rslib.set_option("coupling_compaction_passes", 0)          # whole warps repeat the window
+        st_u1 = rslib.run_batch(uni_single, settings_u, params_u)
+    finally:
+        rslib.set_option("max_points_per_device_batch", 0)
+        rslib.set_option("coupling_compaction_passes", 6)
+    assert np.array_equal(st_u, st_us) and np.array_equal(st_u, st_u1)
+    for k in uni.out:
+        assert np.array_equal(uni.out[k], uni_split.out[k]), k
+        assert np.array_equal(uni.out[k], uni_single.out[k]), k
     # pooled work buffers can be released and are re-created on demand
     rslib.release_workspace()
     again = arrays.copy()
