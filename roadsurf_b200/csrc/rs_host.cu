@@ -78,8 +78,8 @@ int launch_model(const RsArgs& a, const RsArgsCold& ac, const RsModel& m, int we
 {
   const int passes = opt_compaction_passes();
   *launches = 0;
-  if (!(m.use_coupling && wend > 0 && passes > 0 && ac.state && a.scratch && !opt_staging() && a.forcing_step0 == 1 &&
-        a.forcing_mode == 0 && a.step_begin <= 1 && wend + 1 < a.step_end))
+  if (!(m.use_coupling && wend > 0 && passes > 0 && ac.state && a.scratch && !(opt_staging() && a.forcing_mode == 0) &&
+        a.forcing_step0 == 1 && a.step_begin <= 1 && wend + 1 < a.step_end))
   {
     CU(static_cast<cudaError_t>(rs_launch_run(&a, &ac, m.nlayers, opt_staging(), stream, &li->grid, &li->block,
                                               &li->regs_per_thread, &li->smem_bytes)));

@@ -616,3 +616,42 @@ def test_replicated_coupled_points_agree_anywhere_in_a_large_batch(rslib):
     assert passes_big < 0.6 * passes_small, (passes_big, passes_small)   # the compaction did compact
     assert int(big.counters[rslib.CNT_EXECUTED_STEPS]) * base == pytest.approx(
         int(small.counters[rslib.CNT_EXECUTED_STEPS]) * P, rel=0.02)
+
+
+@pytest.mark.gpu
+def test_coarse_records_with_coupling_blank_the_observations_in_the_kernel(rslib, oracle):
+    """Hourly records + coupling on the device: the kernel interpolates in time (JsonSource.cpp:49-176)
+    and blanks TSurfObs over the coupling window as read_input does after the interpolation
+    (roadrunner.cpp:263-274).  Must equal the run on the host-interpolated, host-blanked
+    full-resolution arrays bit for bit, with and without lane compaction, and match the oracle."""
+    import torch
+    npts = 400
+    arrays, settings, params, rec = synth.make_case(npts, 6, seed=71, analysis_hours=5, use_coupling=1,
+                                                     use_relaxation=1, obs_bias=False,
+                                                     settings_kw=dict(coupling_minutes=120))
+    ref = arrays.copy()
+    st_cpu, _ = oracle.run_batch(ref, settings, params, nthreads=8)
+    rslib.set_model(settings, params)
+    full = rslib.DeviceBatch(npts, arrays.sim_len, horizons=True, coupling=True)
+    full.load_point_arrays(arrays)
+    full.run()
+
+    def coarse(state):
+        db = rslib.DeviceBatch(npts, arrays.sim_len, n_records=rec.nrec, coarse=True, horizons=True,
+                               coupling=True, state=state)
+        db.load_records(rec)
+        db.time_fields.copy_(torch.from_numpy(arrays.time))
+        db.load_local(arrays.local, arrays.local_horizons)
+        db.run()
+        torch.cuda.synchronize()
+        return db
+
+    one = coarse(False)                       # single launch
+    assert one.coupling_window_end == 0
+    many = coarse(True)                       # split at the window end, compacted passes
+    assert many.coupling_window_end == arrays.local[0].couplingIndexI
+    assert torch.equal(one.out, full.out) and torch.equal(one.status, full.status)
+    assert torch.equal(many.out, full.out) and torch.equal(many.status, full.status)
+    assert int(many.counters[rslib.CNT_EXECUTED_STEPS]) == int(full.counters[rslib.CNT_EXECUTED_STEPS])
+    _assert_parity(compare(many.outputs(), ref.out), max_mismatch=0.05)
+    assert np.array_equal(many.status.cpu().numpy()[:npts], st_cpu)
