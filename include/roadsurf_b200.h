@@ -366,6 +366,8 @@ typedef struct RsHostBatch
   const double* horizons;     /* [360][npoints] or NULL */
   double* out;                /* [RS_O_NVAR][n_out][npoints], n_out = ceil(sim_len / out_stride) */
   int* status;                /* [npoints] or NULL */
+  int coupling_window_end;    /* as in RsDeviceBatch: 0, or the couplingIndexI every coupled point has
+                                 (enables lane compaction between coupling iterations) */
 } RsHostBatch;
 
 /* Runs a host SoA batch on `ngpus` devices (<= 0: all visible; 1: the current device), points

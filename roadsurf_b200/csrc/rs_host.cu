@@ -713,7 +713,9 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
   } guard{streams, ev};
 
   // per-stream device buffers
-  double *d_forcing[NSTREAM], *d_out[NSTREAM], *d_local[NSTREAM], *d_hor[NSTREAM], *d_scratch[NSTREAM];
+  double *d_forcing[NSTREAM], *d_out[NSTREAM], *d_local[NSTREAM], *d_hor[NSTREAM], *d_scratch[NSTREAM],
+      *d_state[NSTREAM];
+  const int wend = (model.use_coupling && opt_compaction_passes() > 0) ? b->coupling_window_end : 0;
   int* d_status[NSTREAM];
   unsigned long long* d_counters = nullptr;
   int *d_tf = nullptr, *d_rs = nullptr;
@@ -740,6 +742,12 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     }
     CU(pool_get(sh.device, 10 * s + 5, sizeof(int) * chunk, &tmp));
     d_status[s] = static_cast<int*>(tmp);
+    d_state[s] = nullptr;
+    if (wend > 0)
+    {
+      CU(pool_get(sh.device, 10 * s + 6, sizeof(double) * RS_STATE_NPLANES(nl) * chunk, &tmp));
+      d_state[s] = static_cast<double*>(tmp);
+    }
   }
   CU(pool_get(sh.device, 100, sizeof(int) * 6 * b->sim_len, &tmp));
   d_tf = static_cast<int*>(tmp);
@@ -818,10 +826,13 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     ac.counters = d_counters;
     ac.out_start = 0;
     ac.out_nvar = RS_O_NVAR;
-    CU(static_cast<cudaError_t>(
-        rs_launch_run(&a, &ac, nl, opt_staging(), st, &sh.launch.grid, &sh.launch.block, &sh.launch.regs_per_thread,
-                      &sh.launch.smem_bytes)));
-    ++sh.stats.kernel_launches;
+    ac.state = d_state[s];
+    {
+      int n = 0;
+      const int rc = launch_model(a, ac, model, wend, st, &sh.launch, &n);
+      if (rc != RS_OK) return rc;
+      sh.stats.kernel_launches += n;
+    }
     sh.launch.nlayers = nl;
     sh.launch.forcing_mode = b->forcing_mode;
     CU(cudaEventRecord(ev[s][2], st));

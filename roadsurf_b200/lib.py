@@ -74,7 +74,8 @@ class RsHostBatch(C.Structure):
     _fields_ = [("npoints", C.c_int), ("sim_len", C.c_int), ("forcing_mode", C.c_int), ("n_records", C.c_int),
                 ("nvar", C.c_int), ("out_stride", C.c_int),
                 ("forcing", C.c_void_p), ("record_step", C.c_void_p), ("time_fields", C.c_void_p),
-                ("local", C.c_void_p), ("horizons", C.c_void_p), ("out", C.c_void_p), ("status", C.c_void_p)]
+                ("local", C.c_void_p), ("horizons", C.c_void_p), ("out", C.c_void_p), ("status", C.c_void_p),
+                ("coupling_window_end", C.c_int)]
 
 
 class RoadSurfError(RuntimeError):
@@ -175,7 +176,7 @@ def run_batch(arrays, settings, params, ngpus=1):
 
 
 def run_host_soa(settings, params, forcing, time_fields, local, out, record_step=None, horizons=None,
-                 status=None, out_stride=1, ngpus=1):
+                 status=None, out_stride=1, ngpus=1, coupling_window_end=0):
     """roadsurf_run_host_soa on host tensors/arrays (torch CPU tensors -- ideally pinned -- or numpy):
     forcing [n_records, nvar, npoints] f64, time_fields [6, sim_len] i32, local [L_NLOCAL, npoints],
     out [6, n_out, npoints] (written), record_step [n_records] i32 for coarse forcing."""
@@ -190,7 +191,8 @@ def run_host_soa(settings, params, forcing, time_fields, local, out, record_step
     hb = RsHostBatch(npoints=npoints, sim_len=sim_len, forcing_mode=0 if record_step is None else 1,
                      n_records=n_records, nvar=nvar, out_stride=out_stride, forcing=ptr(forcing),
                      record_step=ptr(record_step), time_fields=ptr(time_fields), local=ptr(local),
-                     horizons=ptr(horizons), out=ptr(out), status=ptr(status))
+                     horizons=ptr(horizons), out=ptr(out), status=ptr(status),
+                     coupling_window_end=int(coupling_window_end))
     _check(load().roadsurf_run_host_soa(C.byref(hb), C.byref(settings), C.byref(params), int(ngpus)))
 
 

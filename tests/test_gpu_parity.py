@@ -655,3 +655,37 @@ def test_coarse_records_with_coupling_blank_the_observations_in_the_kernel(rslib
     assert int(many.counters[rslib.CNT_EXECUTED_STEPS]) == int(full.counters[rslib.CNT_EXECUTED_STEPS])
     _assert_parity(compare(many.outputs(), ref.out), max_mismatch=0.05)
     assert np.array_equal(many.status.cpu().numpy()[:npts], st_cpu)
+
+
+@pytest.mark.gpu
+def test_host_soa_entry_matches_device_entry(rslib):
+    """roadsurf_run_host_soa (host structure-of-arrays in, strided outputs back, chunk-pipelined
+    copies) against the device-resident entry on the same data: coarse records with coupling
+    (window asserted -> compacted passes, and not asserted -> single launch), ragged point count."""
+    import torch
+    npts = 1000 + 13
+    arrays, settings, params, rec = synth.make_case(npts, 6, seed=73, analysis_hours=4, use_coupling=1,
+                                                     use_relaxation=1, obs_bias=False,
+                                                     settings_kw=dict(coupling_minutes=90))
+    rslib.set_model(settings, params)
+    db = rslib.DeviceBatch(npts, arrays.sim_len, n_records=rec.nrec, coarse=True, horizons=True,
+                           coupling=True, out_stride=120)
+    db.load_records(rec)
+    db.time_fields.copy_(torch.from_numpy(arrays.time))
+    db.load_local(arrays.local, arrays.local_horizons)
+    db.run()
+    torch.cuda.synchronize()
+    want, want_status = db.out[:, :, :npts].cpu(), db.status[:npts].cpu()
+    h = dict(forcing=db.forcing[:, :, :npts].cpu().contiguous(), time_fields=db.time_fields.cpu(),
+             local=db.local[:, :npts].cpu().contiguous(), horizons=db.horizons[:, :npts].cpu().contiguous(),
+             record_step=db.record_step.cpu())
+    for wend in (0, arrays.local[0].couplingIndexI):
+        out = torch.full((rslib.O_NVAR, db.n_out, npts), 4.0, dtype=torch.float64)
+        status = torch.zeros(npts, dtype=torch.int32)
+        rslib.run_host_soa(settings, params, h["forcing"], h["time_fields"], h["local"], out,
+                           record_step=h["record_step"], horizons=h["horizons"], status=status, out_stride=120,
+                           coupling_window_end=wend)
+        assert torch.equal(out, want), wend
+        assert torch.equal(status, want_status), wend
+        launches = rslib.last_batch_stats()["kernel_launches"]
+        assert (launches > 10) == (wend > 0), (wend, launches)
