@@ -375,6 +375,19 @@ typedef struct RsHostBatch
 int roadsurf_run_host_soa(const RsHostBatch* batch, const InputSettings* settings,
                           const InputParameters* params, int ngpus);
 
+/* roadsurf_read_input_derive for a batch held as coarse records (forcing_mode 1): what read_input
+ * would derive from the time-interpolated arrays (examples/example1/src/roadrunner.cpp:157-278 after
+ * JsonSource.cpp:49-176), computed from the records without materialising them.  Reads
+ * batch->forcing / record_step / npoints / n_records / nvar / sim_len; writes the planes
+ * RS_L_TAIR_RELAX, RS_L_VZ_RELAX, RS_L_RH_RELAX, RS_L_COUPLING_TSURF, RS_L_COUPLING_INDEX,
+ * RS_L_INIT_LEN and RS_L_ACTIVE (1 = all required inputs present at every step) of
+ * `local` [RS_L_NLOCAL][npoints]; lat / lon / sky view are the caller's.  TSurfObs records are NOT
+ * modified: the kernel blanks the coupling window itself.  *window_end (may be NULL) receives the
+ * common couplingIndexI of the coupled points, or 0 if they differ or there are none (the value to
+ * put into coupling_window_end).  Pure host code. */
+int roadsurf_read_input_derive_records(const RsHostBatch* batch, const InputSettings* settings, int forecast_step,
+                                       const int* latest_obs_index, double* local, int* window_end);
+
 /* Pack kernels for callers that hold point-major data on the device:
  * src[point][n] (row stride `src_ld` elements) -> dst plane [n][ld].  Asynchronous. */
 int roadsurf_transpose_to_soa(const double* src, int64_t src_ld, int npoints, int n, double* dst,

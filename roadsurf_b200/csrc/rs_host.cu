@@ -1192,6 +1192,111 @@ int roadsurf_read_input_derive(int npoints, const InputPointers* const* in, cons
   return RS_OK;
 }
 
+int roadsurf_read_input_derive_records(const RsHostBatch* b, const InputSettings* settings, int forecast_step,
+                                       const int* latest_obs_index, double* local, int* window_end)
+{
+  if (!b || !settings || !local || !b->forcing || !b->record_step || b->forcing_mode != 1 || b->n_records < 2 ||
+      b->npoints < 0 || (b->nvar != RS_F_NVAR && b->nvar != RS_F_NVAR_DEPTH))
+    return fail(RS_ERR_BAD_ARGUMENT, "needs a coarse-record host batch");
+  const int sim_len = settings->SimLen, nrec = b->n_records;
+  const size_t np = static_cast<size_t>(b->npoints), nvar = static_cast<size_t>(b->nvar);
+  const double DT = settings->DTSecs;
+  const int span = static_cast<int>(settings->coupling_minutes * 60 / DT);
+  const int* rs = b->record_step;
+  auto rec = [&](int k, int v, size_t p) { return b->forcing[(static_cast<size_t>(k) * nvar + v) * np + p]; };
+  // the value JsonSource's interpolation gives at vector index t (the kernel's fetch_coarse rule)
+  auto value_at = [&](int v, size_t p, int t) {
+    int k = 0;
+    while (k + 2 < nrec && rs[k + 1] <= t) ++k;
+    const double va = rec(k, v, p), vb = rec(k + 1, v, p);
+    if (t == rs[k]) return (va > -100.0) ? va : -9999.9;
+    if (!(va > -100.0 && vb > -100.0)) return -9999.9;
+    const double spn = static_cast<double>(rs[k + 1] - rs[k]) * DT, dt_a = static_cast<double>(t - rs[k]) * DT;
+    return va + (dt_a * (vb - va)) / spn;
+  };
+  // vector indices [lo, hi] served by bracket k (fetch_coarse: the last bracket extends to the end, the
+  // first one back to index 0); false if empty
+  auto bracket_range = [&](int k, int& lo, int& hi) {
+    lo = (k == 0) ? 0 : std::max(rs[k], 0);
+    hi = (k + 2 >= nrec) ? sim_len - 1 : std::min(rs[k + 1] - 1, sim_len - 1);
+    return lo <= hi;
+  };
+  parallel_for(b->npoints, host_threads(), [&](int pi) {
+    const size_t p = static_cast<size_t>(pi);
+    double* L = local + p;
+    // ---- screening.  Bracket k serves the vector indices [lo, hi]; an index above rs[k] needs both
+    // records valid, the index rs[k] itself only record k
+    bool good = true;
+    const int req[6] = {RS_F_TAIR, RS_F_RHZ, RS_F_PREC, RS_F_SW, RS_F_LW, RS_F_VZ};
+    for (int k = 0; k + 1 < nrec && good; ++k)
+    {
+      int lo, hi;
+      if (!bracket_range(k, lo, hi)) continue;
+      const bool at_a = lo <= rs[k] && rs[k] <= hi, above = hi >= std::max(rs[k] + 1, lo);
+      for (int r = 0; r < 6 && good; ++r)
+      {
+        const bool va = rec(k, req[r], p) > -100.0, vb = rec(k + 1, req[r], p) > -100.0;
+        if ((at_a && !va) || (above && !(va && vb))) good = false;
+      }
+    }
+    L[RS_L_ACTIVE * np] = good ? 1.0 : 0.0;
+    if (!good) return;
+    L[RS_L_INIT_LEN * np] = 1 + forecast_step;
+    if (settings->use_relaxation == 1)
+    {
+      L[RS_L_TAIR_RELAX * np] = L[RS_L_VZ_RELAX * np] = L[RS_L_RH_RELAX * np] = -9999.9;
+      const int last = latest_obs_index ? latest_obs_index[pi] : -9999;
+      if (last > -1 && last < sim_len)
+      {
+        L[RS_L_INIT_LEN * np] = last;
+        L[RS_L_TAIR_RELAX * np] = value_at(RS_F_TAIR, p, last);
+        L[RS_L_VZ_RELAX * np] = value_at(RS_F_VZ, p, last);
+        L[RS_L_RH_RELAX * np] = value_at(RS_F_RHZ, p, last);
+      }
+    }
+    if (settings->use_coupling == 1)
+    {
+      L[RS_L_COUPLING_TSURF * np] = -9999.9;
+      L[RS_L_COUPLING_INDEX * np] = -9999;
+      // latest vector index with a valid interpolated observation
+      int i = -1;
+      for (int k = nrec - 2; k >= 0 && i < 0; --k)
+      {
+        int lo, hi;
+        if (!bracket_range(k, lo, hi)) continue;
+        const bool va = rec(k, RS_F_TSURFOBS, p) > -100.0, vb = rec(k + 1, RS_F_TSURFOBS, p) > -100.0;  // NaN fails
+        if (va && vb && hi >= std::max(rs[k] + 1, lo))
+          i = hi;
+        else if (va && lo <= rs[k] && rs[k] <= hi)
+          i = rs[k];
+      }
+      const double obs = (i >= 0) ? value_at(RS_F_TSURFOBS, p, i) : -9999.9;
+      if (i >= span)
+      {
+        L[RS_L_COUPLING_TSURF * np] = obs;
+        L[RS_L_COUPLING_INDEX * np] = i;
+      }
+    }
+  });
+  if (window_end)
+  {
+    int w = 0;
+    bool differs = false;
+    if (settings->use_coupling == 1)
+      for (size_t p = 0; p < np; ++p)
+      {
+        const double ts = local[RS_L_COUPLING_TSURF * np + p], ix = local[RS_L_COUPLING_INDEX * np + p];
+        if (local[RS_L_ACTIVE * np + p] == 0.0 || ts < -100 || ix < 1) continue;
+        if (w == 0)
+          w = static_cast<int>(ix);
+        else if (w != static_cast<int>(ix))
+          differs = true;
+      }
+    *window_end = differs ? 0 : w;
+  }
+  return RS_OK;
+}
+
 void roadsurf_last_batch_stats(RsBatchStats* stats)
 {
   if (stats) *stats = g_stats;

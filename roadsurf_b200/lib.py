@@ -29,7 +29,7 @@ O_NVAR_EXT = 9
 CNT_EXECUTED_STEPS, CNT_BL_ITERATIONS, CNT_COUPLING_PASSES, CNT_FAILED_POINTS, CNT_N = 0, 1, 2, 3, 8
 
 EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roadsurf_run_batch",
-           "roadsurf_run_host_soa", "roadsurf_read_input_derive",
+           "roadsurf_run_host_soa", "roadsurf_read_input_derive", "roadsurf_read_input_derive_records",
            "roadsurf_last_batch_stats", "roadsurf_set_model", "roadsurf_run_device",
            "roadsurf_transpose_to_soa", "roadsurf_transpose_from_soa", "roadsurf_fill",
            "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_set_option", "roadsurf_release_workspace",
@@ -109,6 +109,9 @@ def load():
     lib.roadsurf_run_host_soa.restype = C.c_int
     lib.roadsurf_read_input_derive.argtypes = [C.c_int, P(P(IP)), P(IS), C.c_int, P(C.c_int), P(P(LP)), P(C.c_int)]
     lib.roadsurf_read_input_derive.restype = C.c_int
+    lib.roadsurf_read_input_derive_records.argtypes = [P(RsHostBatch), P(IS), C.c_int, P(C.c_int), C.c_void_p,
+                                                       P(C.c_int)]
+    lib.roadsurf_read_input_derive_records.restype = C.c_int
     lib.roadsurf_last_batch_stats.argtypes = [P(RsBatchStats)]
     lib.roadsurf_set_model.argtypes = [P(IS), P(IPa)]
     lib.roadsurf_set_model.restype = C.c_int
@@ -363,6 +366,24 @@ def read_input_derive(arrays, settings, forecast_step, latest_obs_index=None):
                                              None if lat is None else lat.ctypes.data_as(abi.c_int_p), loc_ptrs,
                                              ok.ctypes.data_as(abi.c_int_p)))
     return ok
+
+
+def read_input_derive_records(forcing, record_step, settings, forecast_step, local, latest_obs_index=None):
+    """roadsurf_read_input_derive_records: forcing [n_records, nvar, npoints] f64 and record_step
+    [n_records] i32 on the host (numpy or CPU tensors); fills the derived planes of local
+    [L_NLOCAL, npoints] in place.  Returns the common coupling window end (0 if none / not common)."""
+    def ptr(x):
+        return x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
+    n_records, nvar, npoints = forcing.shape
+    assert tuple(local.shape) == (L_NLOCAL, npoints)
+    hb = RsHostBatch(npoints=npoints, sim_len=settings.SimLen, forcing_mode=1, n_records=n_records, nvar=nvar,
+                     out_stride=1, forcing=ptr(forcing), record_step=ptr(record_step))
+    lat = None if latest_obs_index is None else np.ascontiguousarray(latest_obs_index, dtype=np.int32)
+    wend = C.c_int(0)
+    _check(load().roadsurf_read_input_derive_records(C.byref(hb), C.byref(settings), int(forecast_step),
+                                                     None if lat is None else lat.ctypes.data_as(abi.c_int_p),
+                                                     C.c_void_p(ptr(local)), C.byref(wend)))
+    return wend.value
 
 
 def release_workspace():

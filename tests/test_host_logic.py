@@ -174,3 +174,61 @@ def test_library_read_input_derive_matches_the_example_logic():
             continue
         assert got == want_local[p], p
         assert np.array_equal(raw.TSurfObs[p], want_obs[p]), p
+
+
+def test_read_input_derive_from_records_equals_derivation_on_interpolated_arrays():
+    """roadsurf_read_input_derive_records (coarse records, nothing materialised) against
+    roadsurf_read_input_derive on the time-interpolated full-resolution arrays: same InitLenI,
+    relaxation targets, coupling index / observation and screening verdicts, bit for bit.  Cases:
+    observations ending at different records, a gap in the middle of the observations, none at all,
+    an isolated last observation, missing required inputs at a record / only between records."""
+    from roadsurf_b200 import lib
+    npts, hours, ana = 48, 5, 6
+    arrays, settings, params, rec = synth.make_case(npts, hours, seed=9, analysis_hours=ana, use_coupling=1,
+                                                     use_relaxation=1, obs_bias=False)
+    rec.TSurfObs[1, :] = -9999.9                    # no observations
+    rec.TSurfObs[2, 5:] = -9999.9                   # observations end two records early
+    rec.TSurfObs[3, 3] = -9999.9                    # a gap in the middle
+    rec.TSurfObs[4, ana] = -9999.9                  # last analysis record missing
+    rec.TSurfObs[6, :ana] = -9999.9                 # only the last observation record is valid
+    rec.TSurfObs[7, :] = -9999.9
+    rec.TSurfObs[7, 1] = -3.25                      # one isolated early observation (< coupling span)
+    rec.tair[8, 4] = -9999.9                        # required input missing at a record
+    rec.VZ[9, rec.nrec - 1] = float("nan")          # ... at the last record (only the extrapolated tail needs it)
+    rec.SW[10, 0] = -9999.9                         # ... at the first record
+    raw, settings, params = synth.case_from_records(rec, hours, ana, 0, 0, coupling_minutes=90)
+    settings.use_coupling, settings.use_relaxation = 1, 1
+    forecast_step = ana * 120
+    latest = np.full(npts, forecast_step + 1, dtype=np.int32)
+    latest[11] = -9999
+    ok = lib.read_input_derive(raw, settings, forecast_step, latest_obs_index=latest)
+
+    forcing = np.zeros((rec.nrec, 11, npts))
+    for v, name in enumerate(synth.RECORD_VARS):
+        forcing[:, v, :] = getattr(rec, name).T
+    local = np.full((lib.L_NLOCAL, npts), 123.0)
+    wend = lib.read_input_derive_records(forcing, rec.record_step.astype(np.int32), settings, forecast_step, local,
+                                         latest_obs_index=latest)
+    assert np.array_equal(local[lib.L_ACTIVE] != 0, ok != 0), (local[lib.L_ACTIVE], ok)
+    assert ok[8] == 0 and ok[10] == 0 and ok.sum() < npts
+    ends = set()
+    for p in range(npts):
+        if not ok[p]:
+            continue
+        lp = raw.local[p]
+        want = (lp.tair_relax, lp.VZ_relax, lp.RH_relax, lp.couplingTsurf, lp.couplingIndexI, lp.InitLenI)
+        got = tuple(local[[lib.L_TAIR_RELAX, lib.L_VZ_RELAX, lib.L_RH_RELAX, lib.L_COUPLING_TSURF,
+                           lib.L_COUPLING_INDEX, lib.L_INIT_LEN], p])
+        assert got == want, (p, got, want)
+        if lp.couplingIndexI > 0:
+            ends.add(lp.couplingIndexI)
+    assert len(ends) > 1 and wend == 0                       # windows differ in this batch
+    assert raw.local[1].couplingIndexI == -9999 and raw.local[7].couplingIndexI == -9999
+    assert raw.local[6].couplingIndexI == forecast_step and raw.local[2].couplingIndexI == 4 * 120
+
+    # a batch with one common window reports it
+    common = np.arange(npts) >= 12
+    local2 = np.full((lib.L_NLOCAL, int(common.sum())), 0.0)
+    wend2 = lib.read_input_derive_records(np.ascontiguousarray(forcing[:, :, common]), rec.record_step.astype(np.int32),
+                                          settings, forecast_step, local2)
+    assert wend2 == forecast_step
