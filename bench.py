@@ -113,17 +113,24 @@ def cpu_arm(args, rec_sample, settings_hours, steps, warmup, threads):
             "sim_len": arrays.sim_len, "ms_per_step": 1e3 * total / len(times)}
 
 
+def first_points(rec, npts):
+    """The first `npts` points of a record sample."""
+    from roadsurf_b200 import synth
+    sub = synth.Records(npts, rec.nrec)
+    for v in synth.RECORD_VARS:
+        setattr(sub, v, getattr(rec, v)[:npts].copy())
+    sub.lat, sub.lon, sub.sky_view = rec.lat[:npts], rec.lon[:npts], rec.sky_view[:npts]
+    sub.horizons, sub.record_step = rec.horizons[:npts], rec.record_step
+    return sub
+
+
 def flops_per_point_step(rec_sample, hours, npts=8):
     """Exact arithmetic-operation count of the reference algorithm on this workload (counting
     scalar in the oracle): each add/mul/div/sqrt/exp/log/trig/pow = 1 flop."""
     from oracle import pyoracle
     from roadsurf_b200 import synth
     import numpy as np
-    sub = synth.Records(npts, rec_sample.nrec)
-    for v in synth.RECORD_VARS:
-        setattr(sub, v, getattr(rec_sample, v)[:npts].copy())
-    sub.lat, sub.lon, sub.sky_view = rec_sample.lat[:npts], rec_sample.lon[:npts], rec_sample.sky_view[:npts]
-    sub.horizons, sub.record_step = rec_sample.horizons[:npts], rec_sample.record_step
+    sub = first_points(rec_sample, npts)
     arrays, settings, params = synth.case_from_records(sub, hours)
     tot, steps = {}, 0
     for p in range(npts):
@@ -298,7 +305,9 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         r = cpu_arm(args, rec_sample, hours, 1, 0, cores)
+        r1 = cpu_arm(args, first_points(rec_sample, min(512, rec_sample.npoints)), hours, 1, 0, 1)
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                        "one_core_value": r1["value"],
                         "sample": f"first {r['points']} points of the GPU workload x {r['sim_len']} steps, "
                                   f"{r['seconds']:.1f} s wall on {cores} threads",
                         "note": "C++ restatement of the Fortran path, reference -Ofast flag set (no gfortran here)"}
