@@ -10,6 +10,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1317,27 +1318,114 @@ int roadsurf_run_batch(int npoints, OutputPointers* const* out, const InputPoint
                      [&](Shard& sh) { return run_shard(sh, out, in, settings, params, local, status); });
 }
 
-void runsimulation(OutputPointers* outPointers, const InputPointers* inPointers, const InputSettings* inSettings,
-                   const InputParameters* inputParam, const LocalParameters* localParam)
+}  // extern "C" (entry points above)
+
+// The reference's mains call runsimulation from a pool of host threads, one point per call
+// (examples/example1/src/roadrunner.cpp:454-496).  One point per launch would leave the GPU at its
+// single-warp latency (~8 us per model step), so concurrent callers are combined: the first caller
+// becomes the leader and runs everything that is queued as ONE batch, the others sleep until their
+// point is done; while a batch is on the device the next one accumulates.  A lone caller pays only a
+// mutex.  Calls with different settings / parameters go into different batches.
+namespace
 {
-  OutputPointers* outs[1] = {outPointers};
-  const InputPointers* ins[1] = {inPointers};
-  const LocalParameters* locs[1] = {localParam};
-  const int rc = roadsurf_run_batch(1, outs, ins, inSettings, inputParam, locs, 1, nullptr);
-  if (rc != RS_OK)
+struct PendingCall
+{
+  OutputPointers* out;
+  const InputPointers* in;
+  const InputSettings* settings;
+  const InputParameters* params;
+  const LocalParameters* local;
+  int rc = RS_OK;
+  bool done = false;
+  std::string err;
+};
+std::mutex g_call_mu;
+std::condition_variable g_call_cv;
+std::vector<PendingCall*> g_call_queue;
+bool g_call_leader = false;
+
+void mark_not_computed(OutputPointers* outPointers, const InputSettings* inSettings)
+{
+  // The reference signature has no error channel: leave the outputs at -9999.0, which is how the
+  // reference marks "not computed" (src/Initialization.f90:397-412).
+  if (!outPointers || !inSettings) return;
+  double* o[RS_O_NVAR] = {outPointers->c_TsurfOut, outPointers->c_SnowOut,    outPointers->c_WaterOut,
+                          outPointers->c_IceOut,   outPointers->c_DepositOut, outPointers->c_Ice2Out};
+  for (int v = 0; v < RS_O_NVAR; ++v)
+    if (o[v])
+      for (int t = 0; t < inSettings->SimLen && t < outPointers->outputLen; ++t) o[v][t] = -9999.0;
+}
+}  // namespace
+
+extern "C" void runsimulation(OutputPointers* outPointers, const InputPointers* inPointers,
+                              const InputSettings* inSettings, const InputParameters* inputParam,
+                              const LocalParameters* localParam)
+{
+  if (!outPointers || !inPointers || !inSettings || !inputParam || !localParam)
   {
-    // The reference signature has no error channel: report and leave the outputs at -9999.0,
-    // which is how the reference marks "not computed" (src/Initialization.f90:397-412).
-    std::fprintf(stderr, "roadsurf_b200 runsimulation failed: %s\n", roadsurf_last_error());
-    if (outPointers && inSettings)
+    std::fprintf(stderr, "roadsurf_b200 runsimulation failed: null argument\n");
+    mark_not_computed(outPointers, inSettings);
+    return;
+  }
+  PendingCall me;
+  me.out = outPointers;
+  me.in = inPointers;
+  me.settings = inSettings;
+  me.params = inputParam;
+  me.local = localParam;
+  std::unique_lock<std::mutex> lk(g_call_mu);
+  g_call_queue.push_back(&me);
+  if (g_call_leader)
+    g_call_cv.wait(lk, [&] { return me.done; });  // a leader is at work: it (or a successor) will run this call
+  else
+  {
+    g_call_leader = true;
+    // callers of a thread pool arrive together: give them a moment to queue up (0.3 ms against a run
+    // of tens of milliseconds), so that the first batch is not a single point
+    g_call_cv.wait_for(lk, std::chrono::microseconds(300), [] { return false; });
+    while (!g_call_queue.empty())
     {
-      double* o[RS_O_NVAR] = {outPointers->c_TsurfOut, outPointers->c_SnowOut,    outPointers->c_WaterOut,
-                              outPointers->c_IceOut,   outPointers->c_DepositOut, outPointers->c_Ice2Out};
-      for (int v = 0; v < RS_O_NVAR; ++v)
-        if (o[v])
-          for (int t = 0; t < inSettings->SimLen && t < outPointers->outputLen; ++t) o[v][t] = -9999.0;
+      // everything queued with the same settings and parameters as the oldest call
+      std::vector<PendingCall*> batch, rest;
+      const PendingCall* first = g_call_queue.front();
+      for (PendingCall* c : g_call_queue)
+      {
+        const bool same = !std::memcmp(c->settings, first->settings, sizeof(InputSettings)) &&
+                          !std::memcmp(c->params, first->params, sizeof(InputParameters));
+        (same ? batch : rest).push_back(c);
+      }
+      g_call_queue.swap(rest);
+      lk.unlock();
+      const int n = static_cast<int>(batch.size());
+      std::vector<OutputPointers*> outs(n);
+      std::vector<const InputPointers*> ins(n);
+      std::vector<const LocalParameters*> locs(n);
+      for (int k = 0; k < n; ++k)
+      {
+        outs[k] = batch[k]->out;
+        ins[k] = batch[k]->in;
+        locs[k] = batch[k]->local;
+      }
+      const int rc = roadsurf_run_batch(n, outs.data(), ins.data(), first->settings, first->params, locs.data(), 1,
+                                        nullptr);
+      const std::string err = (rc != RS_OK) ? std::string(roadsurf_last_error()) : std::string();
+      lk.lock();
+      for (PendingCall* c : batch)
+      {
+        c->rc = rc;
+        c->err = err;
+        c->done = true;
+      }
+      g_call_cv.notify_all();
     }
+    g_call_leader = false;
+  }
+  lk.unlock();
+  if (me.rc != RS_OK)
+  {
+    std::fprintf(stderr, "roadsurf_b200 runsimulation failed: %s\n", me.err.c_str());
+    g_err = me.err;
+    mark_not_computed(outPointers, inSettings);
   }
 }
 
-}  // extern "C"
