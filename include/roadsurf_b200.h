@@ -126,7 +126,9 @@ typedef struct LocalParameters
 
 /* The reference entry point, unchanged (examples/example1/src/Simulation.f90:4-6).  Runs ONE
  * point; kept for unchanged main programs.  It round-trips host<->device per call and is
- * therefore a correctness drop-in, not the fast path: use roadsurf_run_batch. */
+ * therefore a correctness drop-in, not the fast path: use roadsurf_run_batch.  Calls made
+ * concurrently from several host threads (the reference's mains use a thread pool,
+ * examples/example1/src/roadrunner.cpp:454-496) are combined into batches internally. */
 void runsimulation(OutputPointers* outPointers, const InputPointers* inPointers,
                    const InputSettings* inSettings, const InputParameters* inputParam,
                    const LocalParameters* localParam);
