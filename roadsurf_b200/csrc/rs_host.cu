@@ -385,9 +385,16 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
     const size_t per_slot = sizeof(double) * (static_cast<size_t>(sim_len) * (nvar + RS_O_NVAR) + RS_L_NLOCAL +
                                               (any_sky ? 360 : 0) + RS_SCRATCH_NPLANES(nl) +
                                               (wend > 0 ? RS_STATE_NPLANES(nl) : 0)) + sizeof(int);
-    size_t budget = static_cast<size_t>(free_b * 0.80);
-    size_t max_slots = budget / per_slot / 32 * 32;
+    // Two buffer sets are in flight (see the pipeline below), and a large group is cut into at least
+    // four batches so that copying batch b back overlaps packing and uploading batch b+1.
+    const size_t budget = static_cast<size_t>(free_b * 0.80);
+    size_t max_slots = budget / 2 / per_slot / 32 * 32;
     if (max_slots < 32) return fail(RS_ERR_CUDA, "not enough device memory for one warp of points");
+    {
+      const size_t n = slots.size();
+      const size_t parts = n >= 4 * 8192 ? 4 : (n >= 2 * 4096 ? 2 : 1);
+      max_slots = std::min(max_slots, (n / parts + 31) / 32 * 32);
+    }
     if (const int cap = g_opt_max_slots.load()) max_slots = std::min<size_t>(max_slots, (cap + 31) / 32 * 32);
     // staging chunk: <= 192 MiB of pinned memory per direction
     const size_t stage_budget = 192ull << 20;
@@ -408,63 +415,85 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
     CU(static_cast<cudaError_t>(rs_launch_solar(d_tf.as<int>(), sim_len, d_solar.as<double>(), stream)));
     ++sh.stats.kernel_launches;
 
-    for (size_t s0 = 0; s0 < slots.size(); s0 += max_slots)
+    // ---- software pipeline over the device batches: while a helper thread copies batch b back and
+    // scatters it into the caller's arrays (its kernels may still be running), the calling thread packs
+    // and uploads batch b+1 into the other buffer set.  Each set has its own stream.
+    struct Ctx
     {
-      const int ld = static_cast<int>(std::min(max_slots, slots.size() - s0));
-      chunk = std::min(chunk, ld);
       PooledDevice d_forcing, d_out, d_local, d_hor, d_status, d_scratch, d_stage, d_stage2, d_counters, d_state;
-      const int dv = sh.device;
-      CU(d_forcing.alloc(dv, 200, sizeof(double) * sim_len * nvar * ld));
-      CU(d_out.alloc(dv, 201, sizeof(double) * RS_O_NVAR * sim_len * ld));
-      CU(d_local.alloc(dv, 202, sizeof(double) * RS_L_NLOCAL * ld));
-      if (any_sky) CU(d_hor.alloc(dv, 203, sizeof(double) * 360 * ld));
-      CU(d_status.alloc(dv, 204, sizeof(int) * ld));
-      if (model.use_coupling) CU(d_scratch.alloc(dv, 205, sizeof(double) * RS_SCRATCH_NPLANES(nl) * ld));
-      if (wend > 0) CU(d_state.alloc(dv, 211, sizeof(double) * RS_STATE_NPLANES(nl) * ld));
-      const size_t stage_bytes = sizeof(double) * static_cast<size_t>(chunk) * sim_len * std::max(nvar, (int)RS_O_NVAR);
-      CU(d_stage.alloc(dv, 206, stage_bytes));
-      CU(d_stage2.alloc(dv, 207, stage_bytes));
-      CU(d_counters.alloc(dv, 208, sizeof(unsigned long long) * RS_CNT_N));
-      CU(cudaMemsetAsync(d_counters.p, 0, sizeof(unsigned long long) * RS_CNT_N, stream));
       PooledPinned h_stage, h_stage2, h_local, h_hor, h_status;
-      CU(h_stage.alloc(dv, 0, stage_bytes));
-      CU(h_stage2.alloc(dv, 1, stage_bytes));
-      double* h_st[2] = {h_stage.as<double>(), h_stage2.as<double>()};
-      double* d_st[2] = {d_stage.as<double>(), d_stage2.as<double>()};
-      const int nthreads = host_threads();
-      cudaEvent_t ev_free[2];  // staging buffer b may be reused once ev_free[b] has completed
-      for (int b = 0; b < 2; ++b) CU(cudaEventCreateWithFlags(&ev_free[b], cudaEventDisableTiming));
-      struct FreeGuard
+      cudaStream_t st = nullptr;
+      cudaEvent_t ev_free[2] = {nullptr, nullptr};                       // staging buffer reuse
+      cudaEvent_t ev_in0 = nullptr, ev_in1 = nullptr, ev_k1 = nullptr, ev_o1 = nullptr;
+      size_t s0 = 0;
+      int ld = 0, chunk = 0;
+      RsBatchStats out_stats{};   // what the helper thread measured
+      int rc = RS_OK;
+      std::string err;
+      std::thread drain;
+    };
+    Ctx ctx[2];
+    struct CtxGuard  // no thread may outlive its buffers; streams and events are per group
+    {
+      Ctx* c;
+      ~CtxGuard()
       {
-        cudaEvent_t* e;
-        ~FreeGuard()
+        for (int k = 0; k < 2; ++k)
         {
-          cudaEventDestroy(e[0]);
-          cudaEventDestroy(e[1]);
+          if (c[k].drain.joinable()) c[k].drain.join();
+          for (cudaEvent_t e : {c[k].ev_free[0], c[k].ev_free[1], c[k].ev_in0, c[k].ev_in1, c[k].ev_k1, c[k].ev_o1})
+            if (e) cudaEventDestroy(e);
+          if (c[k].st) cudaStreamDestroy(c[k].st);
         }
-      } fguard{ev_free};
-      CU(h_local.alloc(dv, 2, sizeof(double) * RS_L_NLOCAL * ld));
-      if (any_sky) CU(h_hor.alloc(dv, 3, sizeof(double) * 360 * ld));
-      CU(h_status.alloc(dv, 4, sizeof(int) * ld));
+      }
+    } ctx_guard{ctx};
+    const int nthreads = host_threads();
+    const size_t max_ld = std::min(max_slots, slots.size());
+    const size_t nbatches = (slots.size() + max_slots - 1) / max_slots;
+    const int dv = sh.device;
+    for (int k = 0; k < (nbatches > 1 ? 2 : 1); ++k)
+    {
+      Ctx& c = ctx[k];
+      const int o = 50 * k;  // pool slots of the second buffer set
+      CU(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+      for (cudaEvent_t* e : {&c.ev_free[0], &c.ev_free[1]}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+      for (cudaEvent_t* e : {&c.ev_in0, &c.ev_in1, &c.ev_k1, &c.ev_o1}) CU(cudaEventCreate(e));
+      c.chunk = static_cast<int>(std::min<size_t>(chunk, max_ld));
+      CU(c.d_forcing.alloc(dv, 200 + o, sizeof(double) * sim_len * nvar * max_ld));
+      CU(c.d_out.alloc(dv, 201 + o, sizeof(double) * RS_O_NVAR * sim_len * max_ld));
+      CU(c.d_local.alloc(dv, 202 + o, sizeof(double) * RS_L_NLOCAL * max_ld));
+      if (any_sky) CU(c.d_hor.alloc(dv, 203 + o, sizeof(double) * 360 * max_ld));
+      CU(c.d_status.alloc(dv, 204 + o, sizeof(int) * max_ld));
+      if (model.use_coupling) CU(c.d_scratch.alloc(dv, 205 + o, sizeof(double) * RS_SCRATCH_NPLANES(nl) * max_ld));
+      if (wend > 0) CU(c.d_state.alloc(dv, 211 + o, sizeof(double) * RS_STATE_NPLANES(nl) * max_ld));
+      const size_t stage_bytes =
+          sizeof(double) * static_cast<size_t>(c.chunk) * sim_len * std::max(nvar, static_cast<int>(RS_O_NVAR));
+      CU(c.d_stage.alloc(dv, 206 + o, stage_bytes));
+      CU(c.d_stage2.alloc(dv, 207 + o, stage_bytes));
+      CU(c.d_counters.alloc(dv, 208 + o, sizeof(unsigned long long) * RS_CNT_N));
+      CU(c.h_stage.alloc(dv, 0 + o, stage_bytes));
+      CU(c.h_stage2.alloc(dv, 1 + o, stage_bytes));
+      CU(c.h_local.alloc(dv, 2 + o, sizeof(double) * RS_L_NLOCAL * max_ld));
+      if (any_sky) CU(c.h_hor.alloc(dv, 3 + o, sizeof(double) * 360 * max_ld));
+      CU(c.h_status.alloc(dv, 4 + o, sizeof(int) * max_ld));
+    }
+    // the time axis and the solar table were queued on `stream`: every batch stream reads them
+    CU(cudaStreamSynchronize(stream));
+    if (sh.stats.setup_ms == 0.0) sh.stats.setup_ms = now_ms() - setup0 - sh.stats.pack_ms;  // everything so far but packing
 
-      cudaEvent_t ev0, ev1;
-      CU(cudaEventCreate(&ev0));
-      CU(cudaEventCreate(&ev1));
-      struct EvGuard
-      {
-        cudaEvent_t a, b;
-        ~EvGuard()
-        {
-          cudaEventDestroy(a);
-          cudaEventDestroy(b);
-        }
-      } eguard{ev0, ev1};
-
-      sh.stats.setup_ms += now_ms() - setup0 - sh.stats.setup_ms - sh.stats.pack_ms;  // everything so far but packing
-      // ---- per-point statics
+    // ---- input stage (calling thread): statics, then the forcing: caller's per-point arrays -> pinned
+    // [var][point][time] -> device -> SoA.  Rows are packed by all host threads into one of two pinned
+    // buffers while the previous buffer is in flight (H2D copy + device-side transpose).
+    auto stage_in = [&](Ctx& c) -> int {
+      const int ld = c.ld;
+      const size_t s0 = c.s0;
+      cudaStream_t st = c.st;
+      double* h_st[2] = {c.h_stage.as<double>(), c.h_stage2.as<double>()};
+      double* d_st[2] = {c.d_stage.as<double>(), c.d_stage2.as<double>()};
+      CU(cudaMemsetAsync(c.d_counters.p, 0, sizeof(unsigned long long) * RS_CNT_N, st));
       double t0 = now_ms();
       {
-        double* L = h_local.as<double>();
+        double* L = c.h_local.as<double>();
         for (int q = 0; q < ld; ++q)
         {
           const int p = slots[s0 + q];
@@ -484,7 +513,7 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
         }
         if (any_sky)
         {
-          double* H = h_hor.as<double>();
+          double* H = c.h_hor.as<double>();
           for (int q = 0; q < ld; ++q)
           {
             const int p = slots[s0 + q];
@@ -494,68 +523,56 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
         }
       }
       sh.stats.pack_ms += now_ms() - t0;
-      CU(cudaMemcpyAsync(d_local.p, h_local.p, sizeof(double) * RS_L_NLOCAL * ld, cudaMemcpyHostToDevice, stream));
+      CU(cudaEventRecord(c.ev_in0, st));
+      CU(cudaMemcpyAsync(c.d_local.p, c.h_local.p, sizeof(double) * RS_L_NLOCAL * ld, cudaMemcpyHostToDevice, st));
       sh.stats.h2d_bytes += sizeof(double) * RS_L_NLOCAL * ld;
       if (any_sky)
       {
-        CU(cudaMemcpyAsync(d_hor.p, h_hor.p, sizeof(double) * 360 * ld, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(c.d_hor.p, c.h_hor.p, sizeof(double) * 360 * ld, cudaMemcpyHostToDevice, st));
         sh.stats.h2d_bytes += sizeof(double) * 360 * ld;
       }
-
-      // ---- forcing: caller's per-point arrays -> pinned [var][point][time] -> device -> SoA.
-      // Rows are packed by all host threads into one of two pinned buffers while the previous
-      // buffer is in flight (H2D copy + device-side transpose into the SoA tensor).
+      int cidx = 0;
+      for (int q0 = 0; q0 < ld; q0 += c.chunk, ++cidx)
       {
-        const double w0 = now_ms();
-        CU(cudaEventRecord(ev0, stream));
-        int cidx = 0;
-        for (int q0 = 0; q0 < ld; q0 += chunk, ++cidx)
-        {
-          const int npc = std::min(chunk, ld - q0);
-          const int bsel = cidx & 1;
-          if (cidx >= 2) CU(cudaEventSynchronize(ev_free[bsel]));
-          t0 = now_ms();
-          double* S = h_st[bsel];
-          const size_t plane = static_cast<size_t>(npc) * sim_len;
-          parallel_for(npc, nthreads, [&](int q) {
-            const int p = slots[s0 + q0 + q];
-            const size_t row = static_cast<size_t>(q) * sim_len;
-            if (p < 0)
-            {
-              for (int v = 0; v < nvar; ++v) std::memset(S + v * plane + row, 0, sizeof(double) * sim_len);
-              return;
-            }
-            const InputPointers* ip = in[p];
-            const double* src[RS_F_NVAR_DEPTH] = {ip->c_tair, ip->c_tdew, ip->c_VZ,     ip->c_Rhz,
-                                                  ip->c_prec, ip->c_SW,   ip->c_LW,     ip->c_SW_dir,
-                                                  ip->c_LW_net, ip->c_TSurfObs, nullptr, ip->c_Depth};
-            for (int v = 0; v < nvar; ++v)
-            {
-              double* dst = S + v * plane + row;
-              if (v == RS_F_PHASE)
-                for (int t = 0; t < sim_len; ++t) dst[t] = static_cast<double>(ip->c_PrecPhase[t]);
-              else
-                std::memcpy(dst, src[v], sizeof(double) * sim_len);
-            }
-          });
-          sh.stats.pack_ms += now_ms() - t0;
-          const size_t bytes = sizeof(double) * plane * nvar;
-          CU(cudaMemcpyAsync(d_st[bsel], S, bytes, cudaMemcpyHostToDevice, stream));
-          CU(static_cast<cudaError_t>(
-              rs_launch_pack_forcing(d_st[bsel], npc, q0, sim_len, nvar, d_forcing.as<double>(), ld, stream)));
-          CU(cudaEventRecord(ev_free[bsel], stream));
-          ++sh.stats.kernel_launches;
-          sh.stats.h2d_bytes += bytes;
-        }
-        CU(cudaEventRecord(ev1, stream));
-        CU(cudaStreamSynchronize(stream));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ev0, ev1);
-        sh.stats.h2d_ms += ms;  // device-side time of the input phase (copies + transposes, overlapped with packing)
-        (void)w0;
+        const int npc = std::min(c.chunk, ld - q0);
+        const int bsel = cidx & 1;
+        if (cidx >= 2) CU(cudaEventSynchronize(c.ev_free[bsel]));
+        t0 = now_ms();
+        double* S = h_st[bsel];
+        const size_t plane = static_cast<size_t>(npc) * sim_len;
+        parallel_for(npc, nthreads, [&](int q) {
+          const int p = slots[s0 + q0 + q];
+          const size_t row = static_cast<size_t>(q) * sim_len;
+          if (p < 0)
+          {
+            for (int v = 0; v < nvar; ++v) std::memset(S + v * plane + row, 0, sizeof(double) * sim_len);
+            return;
+          }
+          const InputPointers* ip = in[p];
+          const double* src[RS_F_NVAR_DEPTH] = {ip->c_tair, ip->c_tdew, ip->c_VZ,     ip->c_Rhz,
+                                                ip->c_prec, ip->c_SW,   ip->c_LW,     ip->c_SW_dir,
+                                                ip->c_LW_net, ip->c_TSurfObs, nullptr, ip->c_Depth};
+          for (int v = 0; v < nvar; ++v)
+          {
+            double* dst = S + v * plane + row;
+            if (v == RS_F_PHASE)
+              for (int t = 0; t < sim_len; ++t) dst[t] = static_cast<double>(ip->c_PrecPhase[t]);
+            else
+              std::memcpy(dst, src[v], sizeof(double) * sim_len);
+          }
+        });
+        sh.stats.pack_ms += now_ms() - t0;
+        const size_t bytes = sizeof(double) * plane * nvar;
+        CU(cudaMemcpyAsync(d_st[bsel], S, bytes, cudaMemcpyHostToDevice, st));
+        CU(static_cast<cudaError_t>(
+            rs_launch_pack_forcing(d_st[bsel], npc, q0, sim_len, nvar, c.d_forcing.as<double>(), ld, st)));
+        CU(cudaEventRecord(c.ev_free[bsel], st));
+        ++sh.stats.kernel_launches;
+        sh.stats.h2d_bytes += bytes;
       }
+      CU(cudaEventRecord(c.ev_in1, st));
 
-      // ---- the step kernel
+      // ---- the step kernel(s), queued behind the input stage
       RsArgs a;
       std::memset(&a, 0, sizeof a);
       a.npoints = ld;
@@ -570,100 +587,145 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
       a.step_end = sim_len;
       a.forcing_step0 = 1;
       a.out_slot0 = 0;
-      a.forcing = d_forcing.as<double>();
+      a.forcing = c.d_forcing.as<double>();
       a.tf = d_tf.as<int>();
-      a.local = d_local.as<double>();
-      a.horizons = any_sky ? d_hor.as<double>() : nullptr;
+      a.local = c.d_local.as<double>();
+      a.horizons = any_sky ? c.d_hor.as<double>() : nullptr;
       a.solar = d_solar.as<double>();
-      a.out = d_out.as<double>();
-      a.status = d_status.as<int>();
-      a.scratch = model.use_coupling ? d_scratch.as<double>() : nullptr;
+      a.out = c.d_out.as<double>();
+      a.status = c.d_status.as<int>();
+      a.scratch = model.use_coupling ? c.d_scratch.as<double>() : nullptr;
       RsArgsCold ac;
       std::memset(&ac, 0, sizeof ac);
-      ac.counters = d_counters.as<unsigned long long>();
+      ac.counters = c.d_counters.as<unsigned long long>();
       ac.out_start = 0;
       ac.out_nvar = RS_O_NVAR;
-      ac.state = wend > 0 ? d_state.as<double>() : nullptr;
-      CU(cudaEventRecord(ev0, stream));
+      ac.state = wend > 0 ? c.d_state.as<double>() : nullptr;
       {
         int n = 0;
-        const int rc = launch_model(a, ac, model, wend, stream, &sh.launch, &n);
+        const int rc = launch_model(a, ac, model, wend, st, &sh.launch, &n);
         if (rc != RS_OK) return rc;
         sh.stats.kernel_launches += n;
       }
-      CU(cudaEventRecord(ev1, stream));
+      CU(cudaEventRecord(c.ev_k1, st));
       sh.launch.nlayers = nl;
       sh.launch.forcing_mode = 0;
-      CU(cudaStreamSynchronize(stream));
-      {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ev0, ev1);
-        sh.stats.kernel_ms += ms;
-      }
+      return RS_OK;
+    };
 
-      // ---- outputs: SoA -> [var][point][time] -> pinned -> caller's arrays, double buffered: the
-      // host threads scatter chunk c-1 into the caller's arrays while chunk c is copied back
+    // ---- output stage (helper thread): SoA -> [var][point][time] -> pinned -> caller's arrays, double
+    // buffered: chunk c-1 is scattered into the caller's arrays while chunk c is copied back
+    auto stage_out = [&](Ctx& c) -> int {
+      CU(cudaSetDevice(dv));
+      const int ld = c.ld;
+      const size_t s0 = c.s0;
+      cudaStream_t st = c.st;
+      double* h_st[2] = {c.h_stage.as<double>(), c.h_stage2.as<double>()};
+      double* d_st[2] = {c.d_stage.as<double>(), c.d_stage2.as<double>()};
+      RsBatchStats& os = c.out_stats;
+      auto scatter = [&](int q0, int npc, const double* S) {
+        const size_t plane = static_cast<size_t>(npc) * sim_len;
+        parallel_for(npc, nthreads, [&](int q) {
+          const int p = slots[s0 + q0 + q];
+          if (p < 0) return;
+          OutputPointers* op = out[p];
+          double* dst[RS_O_NVAR] = {op->c_TsurfOut, op->c_SnowOut, op->c_WaterOut,
+                                    op->c_IceOut,   op->c_DepositOut, op->c_Ice2Out};
+          for (int v = 0; v < RS_O_NVAR; ++v)
+            std::memcpy(dst[v], S + v * plane + static_cast<size_t>(q) * sim_len, sizeof(double) * sim_len);
+        });
+      };
+      int cidx = 0, prev_q0 = -1, prev_npc = 0;
+      for (int q0 = 0; q0 < ld; q0 += c.chunk, ++cidx)
       {
-        auto scatter = [&](int q0, int npc, const double* S) {
-          const size_t plane = static_cast<size_t>(npc) * sim_len;
-          parallel_for(npc, nthreads, [&](int q) {
-            const int p = slots[s0 + q0 + q];
-            if (p < 0) return;
-            OutputPointers* op = out[p];
-            double* dst[RS_O_NVAR] = {op->c_TsurfOut, op->c_SnowOut, op->c_WaterOut,
-                                      op->c_IceOut,   op->c_DepositOut, op->c_Ice2Out};
-            for (int v = 0; v < RS_O_NVAR; ++v)
-              std::memcpy(dst[v], S + v * plane + static_cast<size_t>(q) * sim_len, sizeof(double) * sim_len);
-          });
-        };
-        CU(cudaEventRecord(ev0, stream));
-        int cidx = 0, prev_q0 = -1, prev_npc = 0;
-        for (int q0 = 0; q0 < ld; q0 += chunk, ++cidx)
-        {
-          const int npc = std::min(chunk, ld - q0);
-          const int bsel = cidx & 1;
-          const size_t bytes = sizeof(double) * static_cast<size_t>(npc) * sim_len * RS_O_NVAR;
-          CU(static_cast<cudaError_t>(rs_launch_unpack_out(d_out.as<double>(), ld, sim_len, q0, npc, d_st[bsel], stream)));
-          ++sh.stats.kernel_launches;
-          CU(cudaMemcpyAsync(h_st[bsel], d_st[bsel], bytes, cudaMemcpyDeviceToHost, stream));
-          CU(cudaEventRecord(ev_free[bsel], stream));
-          sh.stats.d2h_bytes += bytes;
-          if (prev_q0 >= 0)
-          {
-            // buffer of the previous chunk: its copy was enqueued before this one
-            CU(cudaEventSynchronize(ev_free[bsel ^ 1]));
-            t0 = now_ms();
-            scatter(prev_q0, prev_npc, h_st[bsel ^ 1]);
-            sh.stats.unpack_ms += now_ms() - t0;
-          }
-          prev_q0 = q0;
-          prev_npc = npc;
-        }
-        CU(cudaEventRecord(ev1, stream));
+        const int npc = std::min(c.chunk, ld - q0);
+        const int bsel = cidx & 1;
+        const size_t bytes = sizeof(double) * static_cast<size_t>(npc) * sim_len * RS_O_NVAR;
+        CU(static_cast<cudaError_t>(rs_launch_unpack_out(c.d_out.as<double>(), ld, sim_len, q0, npc, d_st[bsel], st)));
+        ++os.kernel_launches;
+        CU(cudaMemcpyAsync(h_st[bsel], d_st[bsel], bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(c.ev_free[bsel], st));
+        os.d2h_bytes += bytes;
         if (prev_q0 >= 0)
         {
-          CU(cudaEventSynchronize(ev_free[(cidx - 1) & 1]));
-          t0 = now_ms();
-          scatter(prev_q0, prev_npc, h_st[(cidx - 1) & 1]);
-          sh.stats.unpack_ms += now_ms() - t0;
+          // buffer of the previous chunk: its copy was enqueued before this one
+          CU(cudaEventSynchronize(c.ev_free[bsel ^ 1]));
+          const double t0 = now_ms();
+          scatter(prev_q0, prev_npc, h_st[bsel ^ 1]);
+          os.unpack_ms += now_ms() - t0;
         }
-        CU(cudaStreamSynchronize(stream));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ev0, ev1);
-        sh.stats.d2h_ms += ms;
+        prev_q0 = q0;
+        prev_npc = npc;
       }
-      CU(cudaMemcpyAsync(h_status.p, d_status.p, sizeof(int) * ld, cudaMemcpyDeviceToHost, stream));
+      CU(cudaEventRecord(c.ev_o1, st));
+      if (prev_q0 >= 0)
+      {
+        CU(cudaEventSynchronize(c.ev_free[(cidx - 1) & 1]));
+        const double t0 = now_ms();
+        scatter(prev_q0, prev_npc, h_st[(cidx - 1) & 1]);
+        os.unpack_ms += now_ms() - t0;
+      }
+      CU(cudaMemcpyAsync(c.h_status.p, c.d_status.p, sizeof(int) * ld, cudaMemcpyDeviceToHost, st));
       unsigned long long cnt[RS_CNT_N];
-      CU(cudaMemcpyAsync(cnt, d_counters.p, sizeof cnt, cudaMemcpyDeviceToHost, stream));
-      CU(cudaStreamSynchronize(stream));
-      sh.stats.d2h_bytes += sizeof(int) * ld;
-      sh.stats.executed_steps += static_cast<int64_t>(cnt[RS_CNT_EXECUTED_STEPS]);
+      CU(cudaMemcpyAsync(cnt, c.d_counters.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c.ev_in0, c.ev_in1);
+      os.h2d_ms += ms;  // device-side time of the input stage (copies + transposes, overlapped with packing)
+      cudaEventElapsedTime(&ms, c.ev_in1, c.ev_k1);
+      os.kernel_ms += ms;
+      cudaEventElapsedTime(&ms, c.ev_k1, c.ev_o1);
+      os.d2h_ms += ms;
+      os.d2h_bytes += sizeof(int) * ld;
+      os.executed_steps += static_cast<int64_t>(cnt[RS_CNT_EXECUTED_STEPS]);
       if (status)
         for (int q = 0; q < ld; ++q)
         {
           const int p = slots[s0 + q];
-          if (p >= 0) status[p] = h_status.as<int>()[q];
+          if (p >= 0) status[p] = c.h_status.as<int>()[q];
         }
+      return RS_OK;
+    };
+    // joins the helper thread of a buffer set and folds its measurements into the shard's
+    auto finish = [&](Ctx& c) -> int {
+      if (!c.drain.joinable()) return RS_OK;
+      c.drain.join();
+      sh.stats.h2d_ms += c.out_stats.h2d_ms;
+      sh.stats.kernel_ms += c.out_stats.kernel_ms;
+      sh.stats.d2h_ms += c.out_stats.d2h_ms;
+      sh.stats.unpack_ms += c.out_stats.unpack_ms;
+      sh.stats.d2h_bytes += c.out_stats.d2h_bytes;
+      sh.stats.executed_steps += c.out_stats.executed_steps;
+      sh.stats.kernel_launches += c.out_stats.kernel_launches;
+      c.out_stats = RsBatchStats{};
+      if (c.rc != RS_OK) return fail(c.rc, c.err);
+      return RS_OK;
+    };
+
+    size_t b = 0;
+    for (size_t s0 = 0; s0 < slots.size(); s0 += max_slots, ++b)
+    {
+      Ctx& c = ctx[b & 1];
+      {
+        const int rc = finish(c);  // the batch that used this buffer set two rounds ago
+        if (rc != RS_OK) return rc;
+      }
+      c.s0 = s0;
+      c.ld = static_cast<int>(std::min(max_slots, slots.size() - s0));
+      {
+        const int rc = stage_in(c);
+        if (rc != RS_OK) return rc;
+      }
+      c.rc = RS_OK;
+      c.drain = std::thread([&stage_out, &c]() {
+        c.rc = stage_out(c);
+        if (c.rc != RS_OK) c.err = g_err;
+      });
+    }
+    for (int k = 0; k < 2; ++k)
+    {
+      const int rc = finish(ctx[k]);
+      if (rc != RS_OK) return rc;
     }
   }
   return RS_OK;
