@@ -511,6 +511,32 @@ def test_multi_gpu_sharding_inside_the_library(rslib):
     for k in arrays.out:
         assert np.array_equal(arrays.out[k], two.out[k]), k
 
+    # the host structure-of-arrays entry shards the same way (coarse records, coupling, strided output)
+    import torch
+    arr, settings, params, rec = synth.make_case(777, 5, seed=49, analysis_hours=3, use_coupling=1,
+                                                 use_relaxation=1, obs_bias=False,
+                                                 settings_kw=dict(coupling_minutes=60))
+    forcing = np.zeros((rec.nrec, 11, 777))
+    for v, name in enumerate(synth.RECORD_VARS):
+        forcing[:, v, :] = getattr(rec, name).T
+    local = np.zeros((rslib.L_NLOCAL, 777))
+    for p in range(777):
+        lp = arr.local[p]
+        local[:, p] = (lp.tair_relax, lp.VZ_relax, lp.RH_relax, lp.couplingTsurf, lp.lat, lp.lon, lp.sky_view,
+                       lp.couplingIndexI, lp.InitLenI, 1.0)
+    hor = np.ascontiguousarray(arr.local_horizons.T)
+    n_out = (arr.sim_len + 59) // 60
+    outs = []
+    for ng in (1, 2):
+        out = np.full((rslib.O_NVAR, n_out, 777), 5.0)
+        st = np.zeros(777, dtype=np.int32)
+        rslib.run_host_soa(settings, params, forcing, arr.time, local, out, record_step=rec.record_step.astype(np.int32),
+                           horizons=hor, status=st, out_stride=60, ngpus=ng,
+                           coupling_window_end=arr.local[0].couplingIndexI)
+        outs.append((out, st))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert (outs[0][0] != 5.0).all()
+
 
 @pytest.mark.gpu
 def test_extended_output_set_with_start_offset(rslib, oracle):
