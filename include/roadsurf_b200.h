@@ -420,6 +420,15 @@ void roadsurf_release_workspace(void);
  * (0 = bounded by free device memory only); batches beyond it are processed one after another. */
 int roadsurf_set_option(const char* name, int value);
 
+/* The kernel evaluates exp and log with the algorithm, operation order and tables of the host's libm
+ * (glibc >= 2.28, FMA code path; roadsurf_b200/csrc/rs_libm.h), so that it is bit-identical to a
+ * reference linked against that libm.  This host-only check compares the same code compiled for the
+ * host with the libm of the running process on `n` random arguments: mismatches[0] (exp) and
+ * mismatches[1] (log) must be 0 for the bit-identity to hold on this machine (another libm version or
+ * a CPU without FMA may differ in the last bit; results then agree to 1 ulp per call, as with any
+ * other libm).  Returns the number of arguments tested per function. */
+long long roadsurf_selftest_libm(long long n, unsigned long long seed, long long* mismatches);
+
 /* Arithmetic self-test on the current device: the kernel's branch-free reciprocal, division and
  * constant-division primitives against the compiler's IEEE division on `n` random operand pairs.
  * mismatches[0..2] receive the number of results that differ (must all be 0); returns the number

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "rs_kernel.cuh"
+#include "rs_libm.h"
 
 namespace
 {
@@ -1185,6 +1186,42 @@ int roadsurf_set_option(const char* name, int value)
     return RS_OK;
   }
   return fail(RS_ERR_BAD_ARGUMENT, "unknown option");
+}
+
+long long roadsurf_selftest_libm(long long n, unsigned long long seed, long long* mismatches)
+{
+  unsigned long long s = seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  auto next = [&]() {
+    s ^= s << 13;
+    s ^= s >> 7;
+    s ^= s << 17;
+    return s;
+  };
+  auto same = [](double a, double b) { return !std::memcmp(&a, &b, sizeof a); };
+  long long bad_e = 0, bad_l = 0;
+  for (long long k = 0; k < n; ++k)
+  {
+    const double u = static_cast<double>(next() >> 11) * 0x1p-53;
+    double x, y;
+    switch (k & 3)
+    {
+      case 0: x = (u - 0.5) * 20; y = 1.0 + u * 0.2; break;               // Magnus exponents; weakly unstable
+      case 1: x = (u - 0.5) * 1000; y = std::ldexp(1.0 + u, static_cast<int>(next() % 600) - 300); break;
+      case 2: x = (u - 0.5) * 1e-3; y = 0.9 + u * 0.2; break;             // around exp(0), log(1)
+      default: x = -u * 6; y = 1.0 + u * 40; break;                       // decays; strongly unstable
+    }
+    bool ok;
+    const double e = rslibm::exp_fast(x, ok);
+    if (ok && !same(e, std::exp(x))) ++bad_e;
+    const double l = rslibm::log_fast(y, ok);
+    if (ok && !same(l, std::log(y))) ++bad_l;
+  }
+  if (mismatches)
+  {
+    mismatches[0] = bad_e;
+    mismatches[1] = bad_l;
+  }
+  return n;
 }
 
 long long roadsurf_selftest_arith(long long n, unsigned long long seed, long long* mismatches)

@@ -32,7 +32,7 @@ EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roa
            "roadsurf_run_host_soa", "roadsurf_read_input_derive", "roadsurf_read_input_derive_records",
            "roadsurf_last_batch_stats", "roadsurf_set_model", "roadsurf_run_device",
            "roadsurf_transpose_to_soa", "roadsurf_transpose_from_soa", "roadsurf_fill",
-           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_set_option", "roadsurf_release_workspace",
+           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_selftest_libm", "roadsurf_set_option", "roadsurf_release_workspace",
            "roadsurf_last_launch",
            "roadsurf_version")
 
@@ -131,6 +131,8 @@ def load():
     lib.roadsurf_set_option.restype = C.c_int
     lib.roadsurf_selftest_arith.argtypes = [C.c_longlong, C.c_ulonglong, P(C.c_longlong)]
     lib.roadsurf_selftest_arith.restype = C.c_longlong
+    lib.roadsurf_selftest_libm.argtypes = [C.c_longlong, C.c_ulonglong, P(C.c_longlong)]
+    lib.roadsurf_selftest_libm.restype = C.c_longlong
     lib.roadsurf_last_launch.argtypes = [P(RsLaunchInfo)]
     _lib = lib
     return lib
@@ -346,6 +348,13 @@ def selftest_arith(n=200_000_000, seed=12345):
     if tested < 0:
         raise RoadSurfError(load().roadsurf_last_error().decode())
     return int(tested), [int(b) for b in bad]
+
+
+def selftest_libm(n=2_000_000, seed=7):
+    """Host-only: [exp, log] mismatch counts of the library's libm-exact exp/log against this process's libm."""
+    bad = (C.c_longlong * 2)()
+    load().roadsurf_selftest_libm(int(n), int(seed), bad)
+    return [int(b) for b in bad]
 
 
 def set_option(name, value):

@@ -753,3 +753,21 @@ def test_host_soa_entry_matches_device_entry(rslib):
         assert torch.equal(status, want_status), wend
         launches = rslib.last_batch_stats()["kernel_launches"]
         assert (launches > 10) == (wend > 0), (wend, launches)
+
+
+@pytest.mark.gpu
+def test_bit_identical_to_the_oracle_where_the_host_libm_is_the_one_the_kernel_mirrors(rslib, oracle):
+    """With exp / log evaluated as the host libm does, the CUDA path reproduces the CPU restatement
+    bit for bit: no tolerance, no flips -- plain forecast with sky-view points, and analysis +
+    forecast with coupling and relaxation.  Skipped where this process's libm is another version."""
+    if rslib.selftest_libm(1_000_000) != [0, 0]:
+        pytest.skip("the host libm differs from the one rs_libm.h mirrors")
+    for kw in (dict(npoints=600, hours=24, seed=81),
+               dict(npoints=600, hours=30, seed=82, analysis_hours=6, use_coupling=1, use_relaxation=1)):
+        arrays, settings, params, _ = synth.make_case(**kw)
+        ref = arrays.copy()
+        st_gpu = rslib.run_batch(arrays, settings, params)
+        st_cpu, _ = oracle.run_batch(ref, settings, params, nthreads=8)
+        assert np.array_equal(st_gpu, st_cpu)
+        for k in ref.out:
+            assert np.array_equal(arrays.out[k], ref.out[k]), (kw, k)
