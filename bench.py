@@ -284,16 +284,16 @@ def main():
     rec_sample = synth_torch.records_sample(db, args.cpu_sample_points or min(8192, 1024 * (os.cpu_count() or 1)))
     flops, per = flops_per_point_step(rec_sample, hours)
     fp64_achieved = flops * P * sim_len / (kernel_ms * 1e-3) / 1e12
-    # DRAM traffic of this kernel from the committed ncu --set full capture (profiles/r01_g_final_ncu_summary.txt:
-    # dram__bytes_read.sum + dram__bytes_write.sum = 943.1 MB for 227 328 points x 2881 steps), scaled to this launch
-    traffic = 943.058432e6 / (227328 * 2881) * P * sim_len if (P >= 151552 and hours == 24) else None
+    # DRAM traffic of this kernel from the committed ncu --set full capture (profiles/r01_h_libm_exact_ncu_summary.txt:
+    # dram__bytes_read.sum + dram__bytes_write.sum = 943.6 MB for 227 328 points x 2881 steps), scaled to this launch
+    traffic = 943.588352e6 / (227328 * 2881) * P * sim_len if (P >= 151552 and hours == 24) else None
     roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": hbm_achieved / hbm_peak, "traffic": traffic,
                 "traffic_source": "ncu capture of the same kernel variant at 227328 points, scaled by point-steps",
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_point_step": alg_bytes / (P * sim_len),
                 "note": "coarse-forcing mode moves ~1.2 B per point-step: this kernel is bound by the fp64 "
-                        "pipe (see roofline_fp64; ncu: fp64 pipe 56 % busy, issue slots 60 %), not by HBM"}
+                        "pipe (see roofline_fp64; ncu: fp64 pipe 54 % busy, issue slots 59 %), not by HBM"}
     roofline_fp64 = {"bound": "fp64", "achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": fp64_achieved / fp64_peak,
                      "peak_source": "DFMA micro-benchmark run live by this script (FMA = 2 flop)",

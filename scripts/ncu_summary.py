@@ -23,6 +23,8 @@ for k in hdr:
         print(f"{k:75s} {m[k]:>18s}")
 print(f"{'warp instructions per warp-step':75s} {float(m['smsp__inst_executed.sum'])/(warps*steps):18.1f}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"], capture_output=True, text=True).stdout
+def num(x):
+    return int(x) if x and x.strip().lstrip('-').isdigit() else 0
 agg, h, cur = [], None, ""
 for r in csv.reader(io.StringIO(src)):
     if not r: continue
@@ -30,7 +32,7 @@ for r in csv.reader(io.StringIO(src)):
     if r[0] == "Line No": h = r; continue
     if h and r[0].isdigit():
         d = dict(zip(h, r))
-        agg.append((cur.split("/")[-1], int(r[0]), r[1].strip()[:84], int(d["Instructions Executed"] or 0), int(d["# Samples"] or 0), int(d["Thread Instructions Executed"] or 0)))
+        agg.append((cur.split("/")[-1], int(r[0]), r[1].strip()[:84], num(d["Instructions Executed"]), num(d["# Samples"]), num(d["Thread Instructions Executed"])))
 tot = sum(a[3] for a in agg) or 1; tots = sum(a[4] for a in agg) or 1
 print(f"\n{'line':>28s} {'inst/warp-step':>14s} {'%inst':>6s} {'%samples':>8s} {'thr/inst':>8s}")
 for a in sorted(agg, key=lambda x: -x[3])[:top]:
