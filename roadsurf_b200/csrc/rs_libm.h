@@ -36,6 +36,23 @@ __device__ const double __align__(16) d_log_tab[256] = RS_LIBM_LOG_TAB;         
 #endif
 static const unsigned long long h_exp_tab[256] = RS_LIBM_EXP_TAB;
 static const double h_log_tab[256] = RS_LIBM_LOG_TAB;
+// scalar coefficients: on the device operands from the constant bank (as literals each costs two
+// move instructions per use and the functions are inlined at several sites), on the host literals
+#if defined(__CUDACC__)
+__constant__ double c_exp_k[8] = {RS_LIBM_EXP_H0, RS_LIBM_EXP_H1, RS_LIBM_EXP_H2, RS_LIBM_EXP_H3,
+                                  RS_LIBM_EXP_H4, RS_LIBM_EXP_H5, RS_LIBM_EXP_H6, RS_LIBM_EXP_H7};
+__constant__ double c_log_k[18] = {RS_LIBM_LOG_H0,  RS_LIBM_LOG_H1,  RS_LIBM_LOG_H2,  RS_LIBM_LOG_H3,  RS_LIBM_LOG_H4,
+                                   RS_LIBM_LOG_H5,  RS_LIBM_LOG_H6,  RS_LIBM_LOG_H7,  RS_LIBM_LOG_H8,  RS_LIBM_LOG_H9,
+                                   RS_LIBM_LOG_H10, RS_LIBM_LOG_H11, RS_LIBM_LOG_H12, RS_LIBM_LOG_H13, RS_LIBM_LOG_H14,
+                                   RS_LIBM_LOG_H15, RS_LIBM_LOG_H16, RS_LIBM_LOG_H17};
+#endif
+#if defined(__CUDA_ARCH__)
+#define RS_EK(i) rslibm::c_exp_k[i]
+#define RS_LK(i) rslibm::c_log_k[i]
+#else
+#define RS_EK(i) RS_LIBM_EXP_H##i
+#define RS_LK(i) RS_LIBM_LOG_H##i
+#endif
 
 RS_LIBM_HD double fma_(double a, double b, double c)
 {
@@ -115,10 +132,10 @@ RS_LIBM_HD double exp_fast(double x, bool& ok)
     ok = false;
     return x;
   }
-  const double InvLn2N = RS_LIBM_EXP_H0, Shift = RS_LIBM_EXP_H1;
-  const double NegLn2hiN = RS_LIBM_EXP_H2, NegLn2loN = RS_LIBM_EXP_H3;
-  const double C2 = RS_LIBM_EXP_H4, C3 = RS_LIBM_EXP_H5, C4 = RS_LIBM_EXP_H6,
-               C5 = RS_LIBM_EXP_H7;
+  const double InvLn2N = RS_EK(0), Shift = RS_EK(1);
+  const double NegLn2hiN = RS_EK(2), NegLn2loN = RS_EK(3);
+  const double C2 = RS_EK(4), C3 = RS_EK(5), C4 = RS_EK(6),
+               C5 = RS_EK(7);
   double kd = fma_(x, InvLn2N, Shift);
   const uint64_t ki = asu(kd);
   kd = add_(kd, -Shift);
@@ -147,16 +164,16 @@ RS_LIBM_HD double log_fast(double x, bool& ok)
   {
     if (ix == 0x3ff0000000000000ull) return 0.0;
     const double r = add_(x, -1.0);
-    const double B0 = RS_LIBM_LOG_H7;
-    const double b12 = fma_(r, RS_LIBM_LOG_H9, RS_LIBM_LOG_H8);     // B1 + r B2
-    const double b45 = fma_(r, RS_LIBM_LOG_H12, RS_LIBM_LOG_H11);   // B4 + r B5
+    const double B0 = RS_LK(7);
+    const double b12 = fma_(r, RS_LK(9), RS_LK(8));     // B1 + r B2
+    const double b45 = fma_(r, RS_LK(12), RS_LK(11));   // B4 + r B5
     const double r2 = mul_(r, r);
-    const double b78 = fma_(r, RS_LIBM_LOG_H15, RS_LIBM_LOG_H14);   // B7 + r B8
-    const double b123 = fma_(r2, RS_LIBM_LOG_H10, b12);
-    const double b456 = fma_(r2, RS_LIBM_LOG_H13, b45);
+    const double b78 = fma_(r, RS_LK(15), RS_LK(14));   // B7 + r B8
+    const double b123 = fma_(r2, RS_LK(10), b12);
+    const double b456 = fma_(r2, RS_LK(13), b45);
     const double r3 = mul_(r, r2);
-    double q = fma_(r2, RS_LIBM_LOG_H16, b78);   // B7 + r B8 + r2 B9
-    q = fma_(r3, RS_LIBM_LOG_H17, q);            // + r3 B10
+    double q = fma_(r2, RS_LK(16), b78);   // B7 + r B8 + r2 B9
+    q = fma_(r3, RS_LK(17), q);            // + r3 B10
     q = fma_(q, r3, b456);
     q = fma_(q, r3, b123);
     // hi + lo = r - r*r/2 in extra precision
@@ -184,9 +201,9 @@ RS_LIBM_HD double log_fast(double x, bool& ok)
   log_entry(i, invc, logc);
   const double z = asd(iz);
   const double kd = static_cast<double>(k);
-  const double Ln2hi = RS_LIBM_LOG_H0, Ln2lo = RS_LIBM_LOG_H1;
-  const double A0 = RS_LIBM_LOG_H2, A1 = RS_LIBM_LOG_H3, A2 = RS_LIBM_LOG_H4,
-               A3 = RS_LIBM_LOG_H5, A4 = RS_LIBM_LOG_H6;
+  const double Ln2hi = RS_LK(0), Ln2lo = RS_LK(1);
+  const double A0 = RS_LK(2), A1 = RS_LK(3), A2 = RS_LK(4),
+               A3 = RS_LK(5), A4 = RS_LK(6);
   const double w = fma_(kd, Ln2hi, logc);
   const double r = fma_(z, invc, -1.0);
   const double a12 = fma_(r, A2, A1);
