@@ -429,6 +429,9 @@ int roadsurf_set_option(const char* name, int value);
  * other libm).  Returns the number of arguments tested per function. */
 long long roadsurf_selftest_libm(long long n, unsigned long long seed, long long* mismatches);
 
+/* Since the library was loaded: runsimulation calls served, and the batches they were combined into. */
+void roadsurf_runsimulation_counters(long long* calls, long long* batches);
+
 /* Arithmetic self-test on the current device: the kernel's branch-free reciprocal, division and
  * constant-division primitives against the compiler's IEEE division on `n` random operand pairs.
  * mismatches[0..2] receive the number of results that differ (must all be 0); returns the number

@@ -1442,6 +1442,7 @@ std::mutex g_call_mu;
 std::condition_variable g_call_cv;
 std::vector<PendingCall*> g_call_queue;
 bool g_call_leader = false;
+std::atomic<long long> g_calls_total{0}, g_call_batches_total{0};
 
 void mark_not_computed(OutputPointers* outPointers, const InputSettings* inSettings)
 {
@@ -1455,6 +1456,12 @@ void mark_not_computed(OutputPointers* outPointers, const InputSettings* inSetti
       for (int t = 0; t < inSettings->SimLen && t < outPointers->outputLen; ++t) o[v][t] = -9999.0;
 }
 }  // namespace
+
+extern "C" void roadsurf_runsimulation_counters(long long* calls, long long* batches)
+{
+  if (calls) *calls = g_calls_total.load();
+  if (batches) *batches = g_call_batches_total.load();
+}
 
 extern "C" void runsimulation(OutputPointers* outPointers, const InputPointers* inPointers,
                               const InputSettings* inSettings, const InputParameters* inputParam,
@@ -1496,6 +1503,8 @@ extern "C" void runsimulation(OutputPointers* outPointers, const InputPointers* 
       g_call_queue.swap(rest);
       lk.unlock();
       const int n = static_cast<int>(batch.size());
+      g_calls_total += n;
+      ++g_call_batches_total;
       std::vector<OutputPointers*> outs(n);
       std::vector<const InputPointers*> ins(n);
       std::vector<const LocalParameters*> locs(n);

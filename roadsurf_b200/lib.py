@@ -32,7 +32,7 @@ EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roa
            "roadsurf_run_host_soa", "roadsurf_read_input_derive", "roadsurf_read_input_derive_records",
            "roadsurf_last_batch_stats", "roadsurf_set_model", "roadsurf_run_device",
            "roadsurf_transpose_to_soa", "roadsurf_transpose_from_soa", "roadsurf_fill",
-           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_selftest_libm", "roadsurf_set_option", "roadsurf_release_workspace",
+           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_selftest_libm", "roadsurf_runsimulation_counters", "roadsurf_set_option", "roadsurf_release_workspace",
            "roadsurf_last_launch",
            "roadsurf_version")
 
@@ -133,6 +133,8 @@ def load():
     lib.roadsurf_selftest_arith.restype = C.c_longlong
     lib.roadsurf_selftest_libm.argtypes = [C.c_longlong, C.c_ulonglong, P(C.c_longlong)]
     lib.roadsurf_selftest_libm.restype = C.c_longlong
+    lib.roadsurf_runsimulation_counters.argtypes = [P(C.c_longlong), P(C.c_longlong)]
+    lib.roadsurf_runsimulation_counters.restype = None
     lib.roadsurf_last_launch.argtypes = [P(RsLaunchInfo)]
     _lib = lib
     return lib
@@ -348,6 +350,13 @@ def selftest_arith(n=200_000_000, seed=12345):
     if tested < 0:
         raise RoadSurfError(load().roadsurf_last_error().decode())
     return int(tested), [int(b) for b in bad]
+
+
+def runsimulation_counters():
+    """(calls served, batches they were combined into) of runsimulation since the library was loaded."""
+    a, b = C.c_longlong(0), C.c_longlong(0)
+    load().roadsurf_runsimulation_counters(C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def selftest_libm(n=2_000_000, seed=7):
