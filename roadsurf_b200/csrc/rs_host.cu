@@ -330,6 +330,13 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
     // slots: windows sorted, each window padded to a warp boundary; uncoupled points fill the gaps
     std::map<long long, std::vector<int>> by_window;
     for (int p : g.points) by_window[window_key(model, *local[p])].push_back(p);
+    // inside a window, points with sky-view radiation go last: the solar geometry and the horizon
+    // lookup are skipped by warps without such a point (7 % on a grid with 30 % of them scattered)
+    for (auto& kv : by_window)
+      std::stable_partition(kv.second.begin(), kv.second.end(), [&](int p) {
+        const double sv = local[p]->sky_view;
+        return !(sv < 1.0 && sv > -0.01f);
+      });
     std::vector<int> slots;  // point index or -1 (padding)
     std::vector<int> loose;
     if (by_window.count(-1)) loose = by_window[-1];
