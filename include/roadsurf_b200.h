@@ -311,6 +311,13 @@ typedef struct RsDeviceBatch
   int out_start;              /* 0-based index of the first stored step (0 <= out_start < sim_len) */
   int out_nvar;               /* 0 or RS_O_NVAR: the six model outputs; RS_O_NVAR_EXT: plus the
                                  Tair / Tdew inputs and the dew point deficit */
+  const int* order;           /* optional [ld] permutation of the point slots (device memory): thread t
+                                 runs point order[t].  Work that only some points need (sky-view
+                                 radiation: solar geometry + horizon lookup) costs a warp as soon as
+                                 one of its 32 points needs it, so gathering such points pays (7 %
+                                 on a grid with 30 % of them scattered); roadsurf_order_points builds
+                                 the permutation.  Results do not depend on it.  Recommended with
+                                 coarse forcing (per-step loads of a permuted warp are gathers). */
   int coupling_window_end;    /* 0, or the caller's assertion that every coupled point of the batch has
                                  couplingIndexI == this value (points that do not are flagged
                                  RS_ST_BAD_WINDOW).  With `state` and `scratch` present it enables lane
@@ -403,6 +410,11 @@ int roadsurf_fill(double* dst, int64_t n, double value, void* stream);
 /* Measure the fp64 FMA throughput of the current device (TFLOP/s, FMA = 2 flop) with a
  * register-resident DFMA kernel; used as the fp64 roofline denominator by bench.py. */
 double roadsurf_measure_fp64_tflops(int iterations);
+
+/* Builds RsDeviceBatch.order on the device: the slots of points without sky-view radiation first, those
+ * with it last, original order kept inside both classes.  `local` is the batch's [RS_L_NLOCAL][ld]
+ * statics tensor, `order` receives ld ints.  Asynchronous on `stream`; call once per batch layout. */
+int roadsurf_order_points(const double* local, int ld, int npoints, int* order, void* stream);
 
 /* roadsurf_run_batch and roadsurf_run_host_soa keep their device and pinned-host work buffers between
  * calls (allocation costs more than a run).  This releases them; they are re-created on demand.  Must

@@ -788,6 +788,7 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
       *d_state[NSTREAM];
   const int wend = (model.use_coupling && opt_compaction_passes() > 0) ? b->coupling_window_end : 0;
   int* d_status[NSTREAM];
+  int* d_order[NSTREAM];
   unsigned long long* d_counters = nullptr;
   int *d_tf = nullptr, *d_rs = nullptr;
   void* tmp = nullptr;
@@ -818,6 +819,12 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     {
       CU(pool_get(sh.device, 10 * s + 6, sizeof(double) * RS_STATE_NPLANES(nl) * chunk, &tmp));
       d_state[s] = static_cast<double*>(tmp);
+    }
+    d_order[s] = nullptr;
+    if (hor && b->forcing_mode == 1)  // sky-view points gathered at one end of the chunk (see roadsurf_order_points)
+    {
+      CU(pool_get(sh.device, 10 * s + 7, sizeof(int) * chunk, &tmp));
+      d_order[s] = static_cast<int*>(tmp);
     }
   }
   CU(pool_get(sh.device, 100, sizeof(int) * 6 * b->sim_len, &tmp));
@@ -898,6 +905,14 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     ac.out_start = 0;
     ac.out_nvar = RS_O_NVAR;
     ac.state = d_state[s];
+    if (d_order[s])
+    {
+      CU(static_cast<cudaError_t>(rs_launch_partition(d_local[s] + static_cast<size_t>(RS_L_SKY_VIEW) * ld, ld, npc, 2,
+                                                      d_order[s], nullptr, st)));
+      ++sh.stats.kernel_launches;
+      ac.index = d_order[s];
+      ac.n_fixed = ld;
+    }
     {
       int n = 0;
       const int rc = launch_model(a, ac, model, wend, st, &sh.launch, &n);
@@ -1105,6 +1120,11 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   ac.counters = b->counters;
   ac.out_start = b->out_start;
   ac.out_nvar = b->out_nvar == RS_O_NVAR_EXT ? RS_O_NVAR_EXT : RS_O_NVAR;
+  if (b->order)
+  {
+    ac.index = b->order;  // thread t runs point order[t]
+    ac.n_fixed = b->ld;
+  }
   RsLaunchInfo li;
   std::memset(&li, 0, sizeof li);
   CU(static_cast<cudaError_t>(rs_launch_solar(b->time_fields, b->sim_len, b->solar, stream)));
@@ -1120,6 +1140,16 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   li.forcing_mode = b->forcing_mode;
   li.launches_total = ++g_launches_total;
   g_launch = li;
+  return RS_OK;
+}
+
+int roadsurf_order_points(const double* local, int ld, int npoints, int* order, void* stream)
+{
+  if (!local || !order || ld < 32 || ld % 32 != 0 || npoints < 0 || npoints > ld)
+    return fail(RS_ERR_BAD_ARGUMENT, "bad arguments");
+  CU(static_cast<cudaError_t>(
+      rs_launch_partition(local + static_cast<size_t>(RS_L_SKY_VIEW) * ld, ld, npoints, 2, order, nullptr, stream)));
+  ++g_launches_total;
   return RS_OK;
 }
 

@@ -39,7 +39,8 @@ struct RsArgsCold
   // Lane compaction between coupling passes (see rs_launch_run_coupled): thread t handles point
   // index[t] for t < *n_index (threads beyond are ghosts that write nothing); null = thread t is point t.
   const int* index;
-  const int* n_index;
+  const int* n_index;            // device-side list length, or null: n_fixed entries
+  int n_fixed;
   int mode;                      // RS_MODE_* bits
   int window_end;                // RS_MODE_SPLIT: the coupling window end every coupled point must have
 };

@@ -32,7 +32,7 @@ EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roa
            "roadsurf_run_host_soa", "roadsurf_read_input_derive", "roadsurf_read_input_derive_records",
            "roadsurf_last_batch_stats", "roadsurf_set_model", "roadsurf_run_device",
            "roadsurf_transpose_to_soa", "roadsurf_transpose_from_soa", "roadsurf_fill",
-           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_selftest_libm", "roadsurf_runsimulation_counters", "roadsurf_set_option", "roadsurf_release_workspace",
+           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_selftest_libm", "roadsurf_runsimulation_counters", "roadsurf_order_points", "roadsurf_set_option", "roadsurf_release_workspace",
            "roadsurf_last_launch",
            "roadsurf_version")
 
@@ -67,7 +67,7 @@ class RsDeviceBatch(C.Structure):
                 ("state", C.c_void_p), ("scratch", C.c_void_p), ("counters", C.c_void_p),
                 ("solar", C.c_void_p), ("step_begin", C.c_int), ("step_end", C.c_int),
                 ("forcing_step0", C.c_int), ("out_slot0", C.c_int), ("out_start", C.c_int),
-                ("out_nvar", C.c_int), ("coupling_window_end", C.c_int)]
+                ("out_nvar", C.c_int), ("order", C.c_void_p), ("coupling_window_end", C.c_int)]
 
 
 class RsHostBatch(C.Structure):
@@ -135,6 +135,8 @@ def load():
     lib.roadsurf_selftest_libm.restype = C.c_longlong
     lib.roadsurf_runsimulation_counters.argtypes = [P(C.c_longlong), P(C.c_longlong)]
     lib.roadsurf_runsimulation_counters.restype = None
+    lib.roadsurf_order_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.roadsurf_order_points.restype = C.c_int
     lib.roadsurf_last_launch.argtypes = [P(RsLaunchInfo)]
     _lib = lib
     return lib
@@ -233,6 +235,7 @@ class DeviceBatch:
         self.out_start = int(out_start)
         self.out_nvar = O_NVAR_EXT if extended_outputs else O_NVAR
         self.coupling_window_end = 0    # set by load_local when all coupled points share one window
+        self.order = None               # optional slot permutation (build_order)
         self.n_out = (self.sim_len - self.out_start + self.out_stride - 1) // self.out_stride
         f64 = dict(dtype=torch.float64, device=device)
         self.forcing = torch.zeros((self.n_records, self.nvar, self.ld), **f64)
@@ -266,8 +269,17 @@ class DeviceBatch:
                              horizons=ptr(self.horizons), out=ptr(out), out_stride=self.out_stride,
                              n_out=out.shape[1], status=ptr(self.status), state=ptr(self.state),
                              scratch=ptr(self.scratch), counters=ptr(self.counters), solar=ptr(self.solar),
-                             out_start=self.out_start, out_nvar=self.out_nvar,
+                             out_start=self.out_start, out_nvar=self.out_nvar, order=ptr(self.order),
                              coupling_window_end=self.coupling_window_end if (step_begin, step_end) == (0, 0) else 0)
+
+    def build_order(self, stream=None):
+        """roadsurf_order_points: gather the points with sky-view radiation at one end of the launch
+        (thread t then runs point order[t]); call after the statics are loaded."""
+        st = stream if stream is not None else self.torch.cuda.current_stream()
+        if self.order is None:
+            self.order = self.torch.empty(self.ld, dtype=self.torch.int32, device=self.local.device)
+        _check(load().roadsurf_order_points(C.c_void_p(self.local.data_ptr()), self.ld, self.npoints,
+                                            C.c_void_p(self.order.data_ptr()), C.c_void_p(st.cuda_stream)))
 
     def run(self, stream=None, **chunk):
         """Asynchronous launch on `stream` (a torch.cuda.Stream; default: the current stream).

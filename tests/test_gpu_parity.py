@@ -768,3 +768,45 @@ def test_bit_identical_to_the_oracle_where_the_host_libm_is_the_one_the_kernel_m
         assert np.array_equal(st_gpu, st_cpu)
         for k in ref.out:
             assert np.array_equal(arrays.out[k], ref.out[k]), (kw, k)
+
+
+@pytest.mark.gpu
+def test_point_order_permutation_does_not_change_results(rslib):
+    """RsDeviceBatch.order (roadsurf_order_points: sky-view points gathered at one end of the launch)
+    changes which thread runs which point and nothing else: coarse forcing, and full-resolution
+    forcing with coupling (order + lane compaction together)."""
+    import torch
+    arrays, settings, params, rec = synth.make_case(1000 + 7, 6, seed=91, sky_view_fraction=0.3)
+    rslib.set_model(settings, params)
+    db = rslib.DeviceBatch(arrays.npoints, arrays.sim_len, n_records=rec.nrec, coarse=True, horizons=True,
+                           out_stride=60)
+    db.load_records(rec)
+    db.time_fields.copy_(torch.from_numpy(arrays.time))
+    db.load_local(arrays.local, arrays.local_horizons)
+    db.run()
+    torch.cuda.synchronize()
+    want, want_status = db.out.clone(), db.status.clone()
+    db.build_order()
+    order = db.order.cpu().numpy()
+    sky = db.local[rslib.L_SKY_VIEW].cpu().numpy() < 1.0
+    sky[arrays.npoints:] = False
+    assert sorted(order.tolist()) == list(range(db.ld))                       # a permutation
+    assert sky[order[:int(sky.sum())]].all() and not sky[order[int(sky.sum()):]].any()
+    db.out.fill_(1.0)
+    db.run()
+    torch.cuda.synchronize()
+    assert torch.equal(db.out, want) and torch.equal(db.status, want_status)
+
+    arrays, settings, params, _ = synth.make_case(500, 4, seed=92, analysis_hours=3, use_coupling=1,
+                                                   use_relaxation=1, settings_kw=dict(coupling_minutes=60))
+    rslib.set_model(settings, params)
+    outs = []
+    for ordered in (False, True):
+        fb = rslib.DeviceBatch(500, arrays.sim_len, horizons=True, coupling=True, state=True)
+        fb.load_point_arrays(arrays)
+        if ordered:
+            fb.build_order()
+        fb.run()
+        torch.cuda.synchronize()
+        outs.append((fb.out.clone(), fb.status.clone(), int(fb.counters[rslib.CNT_EXECUTED_STEPS])))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
