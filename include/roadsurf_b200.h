@@ -161,6 +161,13 @@ enum
   RS_ERR_UNSUPPORTED = -4
 };
 
+/* The examples' default model parameters and settings (examples/example1/src/InputParameters.h:18-110
+ * with the DTSecs-dependent values of InputParameters.cpp:11-22; InputSettings.h:13-23), for callers
+ * that do not read a configuration file.  roadsurf_default_settings zeroes the whole struct first
+ * (also the force_tsurf bytes that the C++ examples leave uninitialised). */
+void roadsurf_default_parameters(InputParameters* params, double DTSecs);
+void roadsurf_default_settings(InputSettings* settings, int SimLen, double DTSecs);
+
 /* Text of the last error on the calling thread ("" if none). */
 const char* roadsurf_last_error(void);
 

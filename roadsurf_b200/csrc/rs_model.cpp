@@ -37,6 +37,57 @@ double campbell_cc(double rhoB, double silt, double wcont)
 }
 }  // namespace
 
+extern "C" void roadsurf_default_parameters(InputParameters* p, double DTSecs)
+{
+  if (!p) return;
+  std::memset(p, 0, sizeof *p);
+  // examples/example1/src/InputParameters.h:18-110
+  p->NightOn = 19.0;  p->NightOff = 4.0;  p->CalmLimDay = 1.5;  p->CalmLimNgt = 0.4;
+  p->TrfFricNgt = 5.0;  p->TrFfricDay = 10.0;
+  p->Grav = 9.81;  p->SB_Const = 5.67e-8;  p->VK_Const = 0.4;  p->LVap = 2.452e6;  p->LFus = 0.334e6;
+  p->WatDens = 999.87;  p->SnowDens = 100.0;  p->IceDens = 920.0;  p->DepDens = 920.0;
+  p->WatMHeat = 333000.0;  p->PorEvaF = 1.0;
+  p->ZRefW = 10.0;  p->ZRefT = 2.0;  p->ZeroDisp = 0.0;  p->ZMom = 0.4;  p->ZHeat = 0.001;
+  p->Emiss = 0.95;  p->Albedo = 0.10;  p->Albedo_surroundings = 0.15;  p->MaxPormms = 1.0;
+  p->TClimG = 6.4;  p->DampDpth = 2.7;  p->Omega = 2.0 * 3.14159265358979323846 / 365.0;  p->AZ = 0.6;
+  p->DampWearF = 0.5;  p->AlbDry = 0.1;  p->AlbSnow = 0.6;
+  p->vsh1 = 1.94e6;  p->vsh2 = 1.28e6;  p->Poro1 = 0.1;  p->Poro2 = 0.4;
+  p->RhoB1 = 2.11;  p->RhoB2 = 1.6;  p->Silt1 = 0.1;  p->Silt2 = 0.8;
+  p->freezing_limit_normal = -0.25;  p->snow_melting_limit_normal = 0.25;  p->ice_melting_limit_normal = 0.25;
+  p->frost_melting_limit_normal = 1.25;  p->frost_formation_limit_normal = 0.25;  p->T4Melt_normal = 0.25;
+  p->TLimColdH = -19.0;  p->TLimColdL = -21.0;  p->WetSnowFormR = 0.1;  p->WetSnowMeltR = 0.6;
+  p->PLimSnow = 0.3;  p->PLimRain = 0.7;
+  p->MaxSnowmms = 100.0;  p->MaxDepmms = 2.0;  p->MaxIcemms = 50.0;  p->MaxExtmms = 1.0;
+  p->MissValI = -9999.0;  p->MissValR = -99.99;  p->Snow2IceFac = 0.5;
+  // examples/example1/src/InputParameters.cpp:11-22
+  p->MinPrecmm = 0.05 * DTSecs / 3600.0;
+  p->MinWatmms = 0.01 * DTSecs / 3600.0;
+  p->MinSnowmms = 0.1 * DTSecs / 3600.0;
+  p->MaxWatmms = p->MaxPormms + p->MaxExtmms;
+  p->WDampLim = 0.1 * p->MaxPormms;
+  p->WWetLim = 0.9 * p->MaxPormms;
+  p->WWearLim = 0.1 * p->MaxPormms;
+  p->MinDepmms = 0.01 * DTSecs / 3600.0;
+  p->MinIcemms = 0.05 * DTSecs / 3600.0;
+}
+
+extern "C" void roadsurf_default_settings(InputSettings* s, int SimLen, double DTSecs)
+{
+  if (!s) return;
+  std::memset(s, 0, sizeof *s);
+  // examples/example1/src/InputSettings.h:13-23
+  s->SimLen = SimLen;
+  s->use_coupling = 0;
+  s->use_relaxation = 0;
+  s->force_tsurf = 0;
+  s->DTSecs = DTSecs;
+  s->tsurfOutputDepth = -9999.9;
+  s->NLayers = 15;
+  s->coupling_minutes = 180;
+  s->couplingEffectReduction = 4.0 * 3600.0;
+  s->outputStep = 60;
+}
+
 int rs_build_model(const InputSettings* s, const InputParameters* p, RsModel* m, char* err, int errlen)
 {
   std::memset(m, 0, sizeof *m);

@@ -32,7 +32,8 @@ EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roa
            "roadsurf_run_host_soa", "roadsurf_read_input_derive", "roadsurf_read_input_derive_records",
            "roadsurf_last_batch_stats", "roadsurf_set_model", "roadsurf_run_device",
            "roadsurf_transpose_to_soa", "roadsurf_transpose_from_soa", "roadsurf_fill",
-           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_selftest_libm", "roadsurf_runsimulation_counters", "roadsurf_order_points", "roadsurf_set_option", "roadsurf_release_workspace",
+           "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_selftest_libm", "roadsurf_runsimulation_counters", "roadsurf_order_points", "roadsurf_default_parameters",
+           "roadsurf_default_settings", "roadsurf_set_option", "roadsurf_release_workspace",
            "roadsurf_last_launch",
            "roadsurf_version")
 
@@ -137,6 +138,10 @@ def load():
     lib.roadsurf_runsimulation_counters.restype = None
     lib.roadsurf_order_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.roadsurf_order_points.restype = C.c_int
+    lib.roadsurf_default_parameters.argtypes = [P(IPa), C.c_double]
+    lib.roadsurf_default_parameters.restype = None
+    lib.roadsurf_default_settings.argtypes = [P(IS), C.c_int, C.c_double]
+    lib.roadsurf_default_settings.restype = None
     lib.roadsurf_last_launch.argtypes = [P(RsLaunchInfo)]
     _lib = lib
     return lib

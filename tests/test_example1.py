@@ -86,3 +86,40 @@ def test_file_pipeline_on_the_gpu_matches_the_cpu_model(tmp_path, rslib, oracle)
     r = compare(a_gpu.out, a_cpu.out)
     assert r["max_dT_matching"] <= T_TOL and r["max_dS_matching"] <= S_TOL and r["mismatch_fraction"] <= 0.15, r
     assert [s["statId"] for s in f_gpu] == [s["statId"] for s in f_cpu]
+
+
+def _build_cpp_example(tmp_path):
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from roadsurf_b200 import build
+    build.build_library()
+    exe = str(tmp_path / "batch_main")
+    libdir = os.path.join(root, "roadsurf_b200")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "batch_main.cpp"), "-o", exe, "-L", libdir, "-lroadsurf_b200",
+                    "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_cpp_example_main_builds_against_the_c_abi_and_reports_a_missing_gpu(tmp_path):
+    """examples/batch_main.cpp (a C++ main shaped like the reference's example1 over the C ABI)
+    compiles with -Wall -Werror against include/roadsurf_b200.h, links the library, derives the
+    per-point parameters on the host and -- without a GPU -- says so and exits 0."""
+    import subprocess
+    import torch
+    exe = _build_cpp_example(tmp_path)
+    r = subprocess.run([exe, "16"], capture_output=True, text=True, timeout=300)
+    assert "coupling window ends at index 360" in r.stdout, r.stdout + r.stderr
+    if not torch.cuda.is_available():
+        assert r.returncode == 0 and "no CUDA device visible" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_example_main_runs_a_coupled_batch(tmp_path):
+    """The same program on a GPU: all points coupled, surface temperature steered to the last
+    observation at the end of the coupling window (exit code 0)."""
+    import subprocess
+    exe = _build_cpp_example(tmp_path)
+    r = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "coupled points 200, failed 0" in r.stdout, r.stdout

@@ -232,3 +232,21 @@ def test_read_input_derive_from_records_equals_derivation_on_interpolated_arrays
     wend2 = lib.read_input_derive_records(np.ascontiguousarray(forcing[:, :, common]), rec.record_step.astype(np.int32),
                                           settings, forecast_step, local2)
     assert wend2 == forecast_step
+
+
+def test_c_abi_defaults_equal_the_python_mirror_of_the_examples_defaults():
+    """roadsurf_default_parameters / roadsurf_default_settings (C) against abi.default_parameters /
+    default_settings (Python): both restate examples/example1/src/InputParameters.{h,cpp} and
+    InputSettings.h; byte-identical structs for several time steps."""
+    import ctypes as C
+    from roadsurf_b200 import lib
+    L = lib.load()
+    for dt in (30.0, 60.0, 7.5):
+        p = abi.InputParameters()
+        C.memset(C.byref(p), 0xAB, C.sizeof(p))
+        L.roadsurf_default_parameters(C.byref(p), dt)
+        assert bytes(p) == bytes(abi.default_parameters(dt)), dt
+        s = abi.InputSettings()
+        C.memset(C.byref(s), 0xAB, C.sizeof(s))
+        L.roadsurf_default_settings(C.byref(s), 2881, dt)
+        assert bytes(s) == bytes(abi.default_settings(2881, dt=dt)), dt
