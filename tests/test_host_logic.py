@@ -250,3 +250,39 @@ def test_c_abi_defaults_equal_the_python_mirror_of_the_examples_defaults():
         C.memset(C.byref(s), 0xAB, C.sizeof(s))
         L.roadsurf_default_settings(C.byref(s), 2881, dt)
         assert bytes(s) == bytes(abi.default_settings(2881, dt=dt)), dt
+
+
+def test_read_input_derive_from_records_randomised_missing_patterns():
+    """Random holes in the observation and forcing records (seeded): the record-based derivation keeps
+    agreeing with the derivation on the interpolated arrays, field by field and bit for bit."""
+    from roadsurf_b200 import lib
+    rng = np.random.default_rng(2024)
+    npts, hours, ana = 64, 4, 5
+    for trial in range(12):
+        arrays, settings, params, rec = synth.make_case(npts, hours, seed=100 + trial, analysis_hours=ana,
+                                                         use_coupling=1, use_relaxation=1, obs_bias=False)
+        holes = rng.random(rec.TSurfObs.shape) < 0.25
+        rec.TSurfObs[holes] = -9999.9
+        for name in ("tair", "VZ", "Rhz", "prec", "SW", "LW"):
+            v = getattr(rec, name)
+            bad = rng.random(v.shape) < 0.004
+            v[bad] = -9999.9 if trial % 2 else float("nan")
+        span_min = int(rng.choice([30, 60, 90, 180]))
+        raw, settings, params = synth.case_from_records(rec, hours, ana, 0, 0, coupling_minutes=span_min)
+        settings.use_coupling, settings.use_relaxation = 1, 1
+        fstep = ana * 120
+        latest = rng.integers(-1, raw.sim_len, size=npts).astype(np.int32)
+        ok = lib.read_input_derive(raw, settings, fstep, latest_obs_index=latest)
+        forcing = np.zeros((rec.nrec, 11, npts))
+        for v, name in enumerate(synth.RECORD_VARS):
+            forcing[:, v, :] = getattr(rec, name).T
+        local = np.zeros((lib.L_NLOCAL, npts))
+        lib.read_input_derive_records(forcing, rec.record_step.astype(np.int32), settings, fstep, local,
+                                      latest_obs_index=latest)
+        assert np.array_equal(local[lib.L_ACTIVE] != 0, ok != 0), trial
+        for p in np.where(ok != 0)[0]:
+            lp = raw.local[p]
+            want = (lp.tair_relax, lp.VZ_relax, lp.RH_relax, lp.couplingTsurf, lp.couplingIndexI, lp.InitLenI)
+            got = tuple(local[[lib.L_TAIR_RELAX, lib.L_VZ_RELAX, lib.L_RH_RELAX, lib.L_COUPLING_TSURF,
+                               lib.L_COUPLING_INDEX, lib.L_INIT_LEN], p])
+            assert got == want, (trial, int(p), got, want)
