@@ -1120,7 +1120,7 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   ac.counters = b->counters;
   ac.out_start = b->out_start;
   ac.out_nvar = b->out_nvar == RS_O_NVAR_EXT ? RS_O_NVAR_EXT : RS_O_NVAR;
-  if (b->order)
+  if (b->order && !(opt_staging() && b->forcing_mode == 0))  // (the staged ring needs consecutive points per warp)
   {
     ac.index = b->order;  // thread t runs point order[t]
     ac.n_fixed = b->ld;
