@@ -81,9 +81,61 @@ def load(fast=False):
     return _libs[name]
 
 
-def run_batch(arrays, settings, params, nthreads=1, fast=False):
+REF_DIR = os.path.join(HERE, "_ref")
+_ref = {}
+
+
+class ReferenceUnavailable(RuntimeError):
+    """oracle/_ref cannot be built here; str(e) is the reason (tests skip WITH it)."""
+
+
+def load_ref(strict=False):
+    """The UNMODIFIED reference built by oracle/build_ref.sh (libroadsurf + example1's Simulation.f90,
+    symbol `runsimulation`).  Raises ReferenceUnavailable with the reason when no Fortran compiler /
+    reference tree exists (the case in this image) and no prebuilt library lies in oracle/_ref/."""
+    name = "libroadsurf_ref_strict.so" if strict else "libroadsurf_ref.so"
+    if name in _ref:
+        return _ref[name]
+    path = os.path.join(REF_DIR, name)
+    if not os.path.exists(path):
+        env = dict(os.environ, REF_FLAVOUR="strict" if strict else "fast")
+        r = subprocess.run(["sh", os.path.join(HERE, "build_ref.sh")], capture_output=True, text=True, env=env)
+        if r.returncode != 0 or not os.path.exists(path):
+            raise ReferenceUnavailable((r.stderr.strip() or r.stdout.strip() or "build_ref.sh failed")
+                                       + f" [exit {r.returncode}]")
+    lib = C.CDLL(path)
+    OP, IP, IS, IPa, LP = (abi.OutputPointers, abi.InputPointers, abi.InputSettings,
+                           abi.InputParameters, abi.LocalParameters)
+    lib.runsimulation.argtypes = [_P(OP), _P(IP), _P(IS), _P(IPa), _P(LP)]
+    lib.runsimulation.restype = None
+    _ref[name] = lib
+    return lib
+
+
+def _run_batch_ref(arrays, settings, params, nthreads, strict):
+    """Point by point through the reference's own runsimulation (re-entrant: all its state is local to
+    the call, examples/example1/src/Simulation.f90:29-46), on `nthreads` Python threads (ctypes drops
+    the GIL).  The reference has no status channel: status is derived from the -9999.0 fill."""
+    import concurrent.futures as cf
+    lib = load_ref(strict)
+    ins, outs = arrays.input_pointers(), arrays.output_pointers()
+
+    def one(p):
+        lib.runsimulation(C.byref(outs[p]), C.byref(ins[p]), C.byref(settings), C.byref(params),
+                          C.byref(arrays.local[p]))
+    with cf.ThreadPoolExecutor(max(1, int(nthreads))) as ex:
+        list(ex.map(one, range(arrays.npoints)))
+    status = np.where(arrays.out["TsurfOut"][:, -1] == -9999.0, 1, 0).astype(np.int32)
+    return status, -1
+
+
+def run_batch(arrays, settings, params, nthreads=1, fast=False, backend="port"):
     """Run every point of a PointArrays through the oracle (mutates arrays' inputs exactly as the
-    reference does, fills arrays.out).  Returns (status[npoints], executed_steps)."""
+    reference does, fills arrays.out).  Returns (status[npoints], executed_steps).
+    backend "port": the C++ restatement (this directory); "ref" / "ref_strict": the unmodified
+    reference from oracle/_ref (raises ReferenceUnavailable when it cannot be built)."""
+    if backend in ("ref", "ref_strict"):
+        return _run_batch_ref(arrays, settings, params, nthreads, backend == "ref_strict")
     lib = load(fast)
     ins = arrays.input_pointers()
     outs = arrays.output_pointers()
