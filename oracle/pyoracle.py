@@ -163,15 +163,15 @@ def count_ops(arrays, settings, params, point=0):
 
 
 TRACE_NAMES = ("Ts_in", "Tair", "Prec", "Q2Melt_in", "rain", "snow", "Snow_preRC", "Wat_preRC", "Ice_preRC",
-               "Q2Melt_preRC", "T1", "T2", "HStor", "BLCond", "LE", "Evap")
+               "Q2Melt_preRC", "T1", "T2", "HStor", "BLCond", "LE", "Evap", "bl_iters", "bl_unstable")
 
 
 def trace_point(arrays, settings, params, point=0):
-    """Per-step internals of one point's oracle run: numpy [sim_len, 16] (columns TRACE_NAMES)."""
+    """Per-step internals of one point's oracle run: numpy [sim_len, 18] (columns TRACE_NAMES)."""
     lib = load(False)
     ins = arrays.input_pointers()
     outs = arrays.output_pointers()
-    tr = np.zeros((arrays.sim_len, 16))
+    tr = np.zeros((arrays.sim_len, len(TRACE_NAMES)))
     lib.oracle_trace_point(C.byref(outs[point]), C.byref(ins[point]), C.byref(settings), C.byref(params),
                            C.byref(arrays.local[point]), tr.ctypes.data_as(abi.c_double_p))
     return tr

@@ -175,6 +175,7 @@ struct Diagnostics
 {
   long long executed_steps = 0;
   long long bl_iterations = 0;
+  long long bl_unstable = 0;
   int coupling_restarts = 0;
   bool bl_not_converged = false;
   bool solar_stop = false;
@@ -186,7 +187,7 @@ struct Diagnostics
   // optional per-step trace [SimLen][TRACE_N] (last visit of a step wins); see roadModelOneStep
   double* trace = nullptr;
 };
-constexpr int TRACE_N = 16;
+constexpr int TRACE_N = 18;
 
 template <class R>
 struct Model
@@ -799,6 +800,7 @@ struct Model
       {
         PSIH = -R(2.0) * r_log((R(1.0) + r_sqrt(R(1.0) - R(16.0) * Stab)) / R(2.0));
         PSIM = F4(0.6) * PSIH;
+        ++diag.bl_unstable;
       }
       ++diag.bl_iterations;
       if (r_abs(BLCond - BLCond_Old) < ConvLim && j >= 5) break;
@@ -1933,6 +1935,8 @@ struct Model
     double* tr = diag.trace ? diag.trace + static_cast<size_t>(input_idxI - 1) * TRACE_N : nullptr;
     if (tr)
     {
+      tr[16] = -static_cast<double>(diag.bl_iterations);
+      tr[17] = -static_cast<double>(diag.bl_unstable);
       tr[0] = r_val(surf.TsurfAve);
       tr[1] = r_val(atm.Tair);
       tr[2] = r_val(atm.PrecInTStep);
@@ -1956,6 +1960,8 @@ struct Model
       tr[13] = r_val(atm.BLCond);
       tr[14] = r_val(atm.LE_Flux);
       tr[15] = r_val(surf.EvapmmTS);
+      tr[16] += static_cast<double>(diag.bl_iterations);  // boundary-layer iterations of this step
+      tr[17] += static_cast<double>(diag.bl_unstable);    // ... of which took the unstable branch
     }
     WearFactors(wearF);
     RoadCond(phy.MaxPormms, wearF);
