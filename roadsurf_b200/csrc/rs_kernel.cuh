@@ -57,9 +57,10 @@ enum
 int rs_upload_model(const RsModel* m);
 int rs_launch_solar(const int* tf, int sim_len, double* table, void* stream);
 int rs_launch_partition(const double* flags_plane, int ld, int npoints, int sorted, int* index, int* n_index, void* stream);
-// `coupling`: the model has use_coupling set (selects the kernel variant compiled with the coupling phase).
-int rs_launch_run(const RsArgs* a, const RsArgsCold* cold, int nlayers, int staged, int coupling, void* stream, int* grid,
-                  int* block, int* regs, int* smem);
+// `coupling`: the model has use_coupling set; `depth`: it has a fixed output depth (depth_mode != 0).  Both select
+// the kernel variant compiled with exactly the features the run needs.
+int rs_launch_run(const RsArgs* a, const RsArgsCold* cold, int nlayers, int staged, int coupling, int depth, void* stream,
+                  int* grid, int* block, int* regs, int* smem);
 int rs_launch_transpose_to_soa(const double* src, long long src_ld, int npoints, int n, double* dst,
                                int ld, void* stream);
 int rs_launch_transpose_from_soa(const double* src, int ld, int npoints, int n, double* dst,
