@@ -353,6 +353,12 @@ enum
 /* Upload settings + parameters for subsequent roadsurf_run_device calls on the current device
  * (derives layer geometry, conductivities and log terms: src/Initialization.f90:181-358,
  * src/BalanceModel.f90:158-186,254-279).  Returns RS_OK or an error. */
+/* Ordering: a device holds ONE model (constant memory).  roadsurf_run_device uses the model of the most
+ * recent roadsurf_set_model on the current device; the batched host entries upload their own.  A model
+ * is only replaced after every kernel queued by roadsurf_run_device under the previous one has finished
+ * (roadsurf_set_model and the host entries block for them), and an identical model is not uploaded
+ * again.  Threads that share a device through the asynchronous entry must therefore agree on its model:
+ * thread A's roadsurf_run_device after thread B's roadsurf_set_model runs B's model. */
 int roadsurf_set_model(const InputSettings* settings, const InputParameters* params);
 
 /* Launch the step kernel over a device-resident batch on `stream` (a cudaStream_t passed as

@@ -40,6 +40,9 @@ def _declare(lib):
     lib.oracle_run_batch.argtypes = [C.c_int, _P(_P(OP)), _P(_P(IP)), _P(IS), _P(IPa), _P(_P(LP)),
                                      C.c_int, _P(C.c_int), _P(C.c_longlong)]
     lib.oracle_run_batch.restype = None
+    lib.oracle_run_batch_state.argtypes = [C.c_int, _P(_P(OP)), _P(_P(IP)), _P(IS), _P(IPa), _P(_P(LP)),
+                                           C.c_int, _P(C.c_int), abi.c_double_p, abi.c_double_p]
+    lib.oracle_run_batch_state.restype = None
     lib.oracle_count_ops.argtypes = [_P(OP), _P(IP), _P(IS), _P(IPa), _P(LP), _P(C.c_ulonglong)]
     lib.oracle_count_ops.restype = C.c_longlong
     lib.oracle_layer_depths.argtypes = [C.c_int, abi.c_double_p]
@@ -148,6 +151,23 @@ def run_batch(arrays, settings, params, nthreads=1, fast=False, backend="port"):
                          loc_ptrs, int(nthreads), status.ctypes.data_as(abi.c_int_p),
                          C.byref(steps))
     return status, steps.value
+
+
+def run_batch_state(arrays, settings, params, nthreads=1):
+    """run_batch that also returns the final state: (status, Tmp[npoints, NLayers+2] = ground%Tmp(0:N+1),
+    surf[npoints, 10] = TsurfAve, Wat, Snow, Ice, Ice2, Dep, Q2Melt, T4Melt, EvapmmTS, Albedo)."""
+    lib = load(False)
+    ins, outs = arrays.input_pointers(), arrays.output_pointers()
+    in_ptrs = abi.pointer_arrays(ins, abi.InputPointers)
+    out_ptrs = abi.pointer_arrays(outs, abi.OutputPointers)
+    loc_ptrs = abi.pointer_arrays(arrays.local, abi.LocalParameters)
+    status = np.zeros(arrays.npoints, dtype=np.int32)
+    tmp = np.zeros((arrays.npoints, settings.NLayers + 2))
+    surf = np.zeros((arrays.npoints, 10))
+    lib.oracle_run_batch_state(arrays.npoints, out_ptrs, in_ptrs, C.byref(settings), C.byref(params), loc_ptrs,
+                               int(nthreads), status.ctypes.data_as(abi.c_int_p), tmp.ctypes.data_as(abi.c_double_p),
+                               surf.ctypes.data_as(abi.c_double_p))
+    return status, tmp, surf
 
 
 def count_ops(arrays, settings, params, point=0):

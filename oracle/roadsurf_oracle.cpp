@@ -136,6 +136,50 @@ void oracle_run_batch(int npoints, OutputPointers* const* out, const InputPointe
   if (executed_steps) *executed_steps = steps.load();
 }
 
+// oracle_run_batch that also returns every point's final ground temperature profile and surface state:
+// tmp_out[p][0..N+1] = ground%Tmp(0:N+1) after the last step, surf_out[p][0..9] = TsurfAve, SrfWatmms,
+// SrfSnowmms, SrfIcemms, SrfIce2mms, SrfDepmms, Q2Melt, T4Melt, EvapmmTS, Albedo (the order of the
+// kernel's state planes).  For the parity tests of the ground-layer temperatures.
+void oracle_run_batch_state(int npoints, OutputPointers* const* out, const InputPointers* const* in,
+                            const InputSettings* settings, const InputParameters* params,
+                            const LocalParameters* const* local, int nthreads, int* status, double* tmp_out,
+                            double* surf_out)
+{
+  if (nthreads < 1) nthreads = 1;
+  std::atomic<int> next(0);
+  auto worker = [&]() {
+    for (;;)
+    {
+      const int p = next.fetch_add(1);
+      if (p >= npoints) break;
+      Model<double> m;
+      m.runsimulation(*out[p], *in[p], *settings, *params, *local[p]);
+      if (status) status[p] = status_word(m);
+      const int nl = m.settings.NLayers;
+      if (tmp_out)
+        for (int j = 0; j <= nl + 1; ++j) tmp_out[static_cast<size_t>(p) * (nl + 2) + j] = m.ground.Tmp[j];
+      if (surf_out)
+      {
+        double* o = surf_out + static_cast<size_t>(p) * 10;
+        o[0] = m.surf.TsurfAve;
+        o[1] = m.surf.SrfWatmms;
+        o[2] = m.surf.SrfSnowmms;
+        o[3] = m.surf.SrfIcemms;
+        o[4] = m.surf.SrfIce2mms;
+        o[5] = m.surf.SrfDepmms;
+        o[6] = m.surf.Q2Melt;
+        o[7] = m.surf.T4Melt;
+        o[8] = m.surf.EvapmmTS;
+        o[9] = m.ground.Albedo;
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+  worker();
+  for (auto& t : pool) t.join();
+}
+
 // Run one point with the op-counting scalar.  counts[9] = add, mul, div, sqrt, exp, log, trig,
 // pow, cmp; returns the number of executed steps.
 long long oracle_count_ops(OutputPointers* out, const InputPointers* in, const InputSettings* settings,

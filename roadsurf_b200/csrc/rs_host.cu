@@ -29,8 +29,19 @@ namespace
 thread_local std::string g_err;
 thread_local RsBatchStats g_stats;
 thread_local RsLaunchInfo g_launch;
+// The model of a device lives in one __constant__ symbol (rs_kernel.cu).  Ordering rule: the symbol is
+// only ever overwritten (a) with DIFFERENT bytes and (b) after every kernel that was launched through
+// roadsurf_run_device since the previous upload has finished (the asynchronous entry records an event
+// per stream; the host entries synchronise their own streams before they return and hold
+// g_device_mu while they run).  An upload of identical bytes is skipped.
+struct DeviceModel
+{
+  RsModel m;
+  bool valid = false;
+  std::map<cudaStream_t, cudaEvent_t> last_launch;  // per caller stream: after its latest step kernel
+};
 std::mutex g_model_mu;
-std::map<int, RsModel> g_models;  // device -> model currently in its constant memory
+std::map<int, DeviceModel> g_models;  // device -> model currently in its constant memory
 std::atomic<int> g_launches_total{0};
 
 // Run-time options (roadsurf_set_option).  forcing_staging: 1 = full-resolution forcing through the
@@ -137,12 +148,30 @@ int set_model_on_current_device(const InputSettings* settings, const InputParame
   if (rc != RS_OK) return fail(rc, err);
   int dev = 0;
   CU(cudaGetDevice(&dev));
-  CU(static_cast<cudaError_t>(rs_upload_model(&m)));
   {
     std::lock_guard<std::mutex> lk(g_model_mu);
-    g_models[dev] = m;
+    DeviceModel& dm = g_models[dev];
+    if (!dm.valid || std::memcmp(&dm.m, &m, sizeof m) != 0)
+    {
+      // kernels of the asynchronous entry may still be reading the old model: wait for them
+      for (auto& kv : dm.last_launch) CU(cudaEventSynchronize(kv.second));
+      CU(static_cast<cudaError_t>(rs_upload_model(&m)));
+      dm.m = m;
+      dm.valid = true;
+    }
   }
   if (out) *out = m;
+  return RS_OK;
+}
+
+// roadsurf_run_device: remember that `stream` has kernels in flight that read the device's model.
+int note_async_launch(int dev, cudaStream_t stream)
+{
+  std::lock_guard<std::mutex> lk(g_model_mu);
+  DeviceModel& dm = g_models[dev];
+  cudaEvent_t& ev = dm.last_launch[stream];
+  if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CU(cudaEventRecord(ev, stream));
   return RS_OK;
 }
 
@@ -1052,8 +1081,9 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   {
     std::lock_guard<std::mutex> lk(g_model_mu);
     auto it = g_models.find(dev);
-    if (it == g_models.end()) return fail(RS_ERR_BAD_ARGUMENT, "roadsurf_set_model was not called on this device");
-    m = it->second;
+    if (it == g_models.end() || !it->second.valid)
+      return fail(RS_ERR_BAD_ARGUMENT, "roadsurf_set_model was not called on this device");
+    m = it->second.m;
   }
   if (b->ld < 32 || b->ld % 32 != 0 || b->npoints < 0 || b->npoints > b->ld)
     return fail(RS_ERR_BAD_ARGUMENT, "ld must be a positive multiple of 32 and >= npoints");
@@ -1135,6 +1165,10 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
     const int rc = launch_model(a, ac, m, b->coupling_window_end, stream, &li, &n);
     if (rc != RS_OK) return rc;
     g_launches_total += n - 1;  // (the last one is counted below)
+  }
+  {
+    const int rc = note_async_launch(dev, static_cast<cudaStream_t>(stream));
+    if (rc != RS_OK) return rc;
   }
   li.nlayers = m.nlayers;
   li.forcing_mode = b->forcing_mode;
@@ -1345,25 +1379,28 @@ int roadsurf_read_input_derive_records(const RsHostBatch* b, const InputSettings
   auto value_at = [&](int v, size_t p, int t) {
     int k = 0;
     while (k + 2 < nrec && rs[k + 1] <= t) ++k;
+    if (t >= rs[nrec - 1]) return -9999.9;  // at / after the last record: never filled (JsonSource.cpp:85)
     const double va = rec(k, v, p), vb = rec(k + 1, v, p);
     if (t == rs[k]) return (va > -100.0) ? va : -9999.9;
     if (!(va > -100.0 && vb > -100.0)) return -9999.9;
     const double spn = static_cast<double>(rs[k + 1] - rs[k]) * DT, dt_a = static_cast<double>(t - rs[k]) * DT;
     return va + (dt_a * (vb - va)) / spn;
   };
-  // vector indices [lo, hi] served by bracket k (fetch_coarse: the last bracket extends to the end, the
-  // first one back to index 0); false if empty
+  // vector indices [lo, hi] served by bracket k (the first one reaches back to index 0); false if empty.
+  // Indices at or after the last record are served by nobody: the reference's interpolation stops at its
+  // last raw record (JsonSource.cpp:85), those steps stay missing and read_input rejects the point.
   auto bracket_range = [&](int k, int& lo, int& hi) {
     lo = (k == 0) ? 0 : std::max(rs[k], 0);
-    hi = (k + 2 >= nrec) ? sim_len - 1 : std::min(rs[k + 1] - 1, sim_len - 1);
+    hi = std::min(rs[k + 1] - 1, sim_len - 1);
     return lo <= hi;
   };
+  const bool records_cover_run = rs[nrec - 1] > sim_len - 1;
   parallel_for(b->npoints, host_threads(), [&](int pi) {
     const size_t p = static_cast<size_t>(pi);
     double* L = local + p;
     // ---- screening.  Bracket k serves the vector indices [lo, hi]; an index above rs[k] needs both
     // records valid, the index rs[k] itself only record k
-    bool good = true;
+    bool good = records_cover_run;
     const int req[6] = {RS_F_TAIR, RS_F_RHZ, RS_F_PREC, RS_F_SW, RS_F_LW, RS_F_VZ};
     for (int k = 0; k + 1 < nrec && good; ++k)
     {

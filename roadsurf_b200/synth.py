@@ -131,14 +131,16 @@ def draw_records(npoints, nrec, seed, start, record_secs=3600, dt_secs=30.0, fir
 
 def interpolate_records(rec, sim_len, dt_secs=30.0):
     """Records -> per-step arrays, following JsonSource.cpp:49-176 for a record grid that starts
-    at or before step 0 and extends beyond the last step.  Times are integer seconds there, so the
+    at or before step 0.  Steps at or after the LAST record are left missing, as the reference's loop
+    leaves them (`rawPos+1<rawLen`, JsonSource.cpp:85).  Times are integer seconds there, so the
     weights are formed from seconds, not steps (the rounding differs).  Returns dict name ->
     [npoints, sim_len] (PrecPhase as int32)."""
     steps = np.arange(sim_len, dtype=np.int64)
     rs = rec.record_step.astype(np.int64)
-    if rs[0] > 0 or rs[-1] <= sim_len - 1:
-        raise ValueError("records must bracket the simulation (first <= step 0, last > last step)")
-    k = np.searchsorted(rs, steps, side="right") - 1  # rs[k] <= step < rs[k+1]
+    if rs[0] > 0:
+        raise ValueError("the first record must lie at or before step 0")
+    beyond = steps >= rs[-1]
+    k = np.minimum(np.searchsorted(rs, steps, side="right") - 1, len(rs) - 2)  # rs[k] <= step < rs[k+1]
     dt_a = (steps - rs[k]).astype(np.float64) * dt_secs
     span = (rs[k + 1] - rs[k]).astype(np.float64) * dt_secs
     exact = (steps == rs[k])
@@ -148,14 +150,14 @@ def interpolate_records(rec, sim_len, dt_secs=30.0):
         b = getattr(rec, v)[:, k + 1]
         if v == "PrecPhase":
             val = np.where(exact[None, :], a, b)
-            out[v] = np.where(val > -100.0, val, -9999.0).astype(np.int32)
+            out[v] = np.where((val > -100.0) & ~beyond[None, :], val, -9999.0).astype(np.int32)
             continue
         miss = -1000.0 if v == "LW_net" else -100.0
         interp = a + (dt_a[None, :] * (b - a)) / span[None, :]
         ok_between = (a > miss) & (b > miss)
         val = np.where(exact[None, :], np.where(a > miss, a, -9999.9),
                        np.where(ok_between, interp, -9999.9))
-        out[v] = val
+        out[v] = np.where(beyond[None, :], -9999.9, val)
     return out
 
 

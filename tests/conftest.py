@@ -27,3 +27,16 @@ def rslib():
     if lib.load().roadsurf_device_count() < 1:
         pytest.fail("no CUDA device visible to libroadsurf_b200.so")
     return lib
+
+
+@pytest.fixture(scope="session")
+def exact(rslib):
+    """Bit-identity with the oracle needs the host libm to be the one roadsurf_b200/csrc/rs_libm.h mirrors
+    (glibc's exp / log, FMA code path).  On a box where it is not, the exact tests FAIL with this message
+    -- they do not skip: a silent skip would hide a regression to the 0.5-1.3 % flip regime."""
+    bad = rslib.selftest_libm(2_000_000)
+    if bad != [0, 0]:
+        pytest.fail(f"host libm differs from the one rs_libm.h mirrors (exp/log mismatches {bad} of 2e6): "
+                    "the CUDA path cannot be bit-identical to the oracle on this machine; regenerate "
+                    "rs_libm_tables.h with scripts/gen_libm_tables.py for this glibc")
+    return True

@@ -16,7 +16,12 @@ def compare(out_a, out_b):
         dS = np.maximum(dS, np.abs(out_a[n] - out_b[n]))
     bad = (dT.max(axis=1) > T_TOL) | (dS.max(axis=1) > S_TOL)
     good = ~bad
+    differing = 0
+    for n in ("TsurfOut",) + STORAGES:
+        differing += int((~((out_a[n] == out_b[n]) | (np.isnan(out_a[n]) & np.isnan(out_b[n])))).sum())
     res = {
+        "bit_identical": differing == 0,
+        "differing_values": differing,
         "npoints": int(dT.shape[0]),
         "mismatch_points": int(bad.sum()),
         "mismatch_fraction": float(bad.mean()),

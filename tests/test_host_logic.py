@@ -286,3 +286,39 @@ def test_read_input_derive_from_records_randomised_missing_patterns():
             got = tuple(local[[lib.L_TAIR_RELAX, lib.L_VZ_RELAX, lib.L_RH_RELAX, lib.L_COUPLING_TSURF,
                                lib.L_COUPLING_INDEX, lib.L_INIT_LEN], p])
             assert got == want, (trial, int(p), got, want)
+
+
+def test_records_ending_inside_the_run_fail_the_screening_like_read_input():
+    """JsonSource's interpolation leaves every step at or after its last raw record missing
+    (JsonSource.cpp:85), and read_input then rejects the point (roadrunner.cpp:167-195).  The coarse-record
+    derivation does the same, and agrees with the derivation on arrays interpolated by the example's rule
+    (roadsurf_b200/example1.py::interpolate)."""
+    from roadsurf_b200 import example1, lib
+    npts, hours = 5, 4
+    arrays, settings, params, rec = synth.make_case(npts, hours, seed=12)
+    forcing = np.zeros((rec.nrec, 11, npts))
+    for v, name in enumerate(synth.RECORD_VARS):
+        forcing[:, v, :] = getattr(rec, name).T
+    rs = rec.record_step.astype(np.int32)
+    local = np.zeros((lib.L_NLOCAL, npts))
+    lib.read_input_derive_records(forcing, rs, settings, 0, local)
+    assert (local[lib.L_ACTIVE] == 1).all()                  # records reach beyond the last step: fine
+    for cut in (1, 2):                                       # last record == last step, and before it
+        f2, r2 = np.ascontiguousarray(forcing[:rec.nrec - cut]), np.ascontiguousarray(rs[:rec.nrec - cut])
+        assert r2[-1] <= settings.SimLen - 1
+        lib.read_input_derive_records(f2, r2, settings, 0, local)
+        assert (local[lib.L_ACTIVE] == 0).all(), cut
+        # the example's own rule: the tail of the interpolated series is missing
+        simtime = 30 * np.arange(settings.SimLen)
+        tair = example1.interpolate(30 * r2.astype(np.int64), f2[:, 0, 0], simtime)
+        assert (tair[int(r2[-1]):] < -9000).all() and tair[int(r2[-1]) - 1] > -100
+        fields_tail = synth.interpolate_records(_short_records(rec, cut), settings.SimLen)["tair"][0]
+        assert np.array_equal(fields_tail, tair)
+
+
+def _short_records(rec, cut):
+    short = synth.Records(rec.npoints, rec.nrec - cut)
+    for v in synth.RECORD_VARS:
+        setattr(short, v, getattr(rec, v)[:, :rec.nrec - cut].copy())
+    short.record_step = rec.record_step[:rec.nrec - cut]
+    return short
