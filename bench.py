@@ -2,21 +2,33 @@
 """Benchmark of the RoadSurf per-point simulation loop on B200.
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
+                    [--workload c4|c3|c5] [--scaling weak|strong] [--inproc]
 
-Workload (config.workload): BASELINE.json config 4, "synthetic 10^7-point km-scale road grid, 24 h
-forecast, sharded across 1/2/4/8 B200": every GPU runs one 1.25e6-point shard (10^7 / 8), so at
-N = 8 the job is exactly the named configuration ("weak" scaling).  SimLen = 2881 steps of 30 s,
-15 ground layers, hourly forcing records interpolated on the device, hourly outputs, 30 % of the
-points with sky-view / shadow radiation.  One bench "step" = one full 24 h pass over the shard
-(= one launch of the step kernel).
+Workloads (BASELINE.json configs; `config.workload` in the output names the one that ran):
+  c4 (default)  "synthetic 10^7-point km-scale road grid, 24 h forecast, sharded across 1/2/4/8 B200":
+                SimLen 2881 steps of 30 s, 15 ground layers, hourly forcing records interpolated on the
+                device, hourly outputs, 30 % of the points with sky-view / shadow radiation.
+                weak (default): every GPU runs one 1.25e6-point shard (10^7 / 8), so at N = 8 the job is
+                exactly the named configuration; at N = 1 the FULL 10^7-point configuration (it fits one
+                B200: ~65 GB) is also run once and reported as `full_config`.
+                strong: the 10^7 points are split over the N GPUs.
+  c3            "synthetic 10^5-point national road network, 48 h forecast ... with Coupling/Relaxation":
+                6 h analysis + 48 h forecast (SimLen 6481), coupling window 180 min, from hourly records;
+                weak = one 10^5-point replica per GPU, strong = 10^5 points split over the GPUs.
+  c5            "51-member ensemble x 10^6 points (5.1e7 point-runs), 48 h, full 8xB200 box": SimLen 5761;
+                weak = 5.1e7 / 8 = 6.375e6 point-runs per GPU.
+One bench "step" = one full pass over the rank's points (one launch of the step kernel, several for c3).
 
 metric  road-point-timesteps/s = points * SimLen / seconds (nominal model steps).
 value   kernel-resident throughput: inputs already in HBM when the timed region starts.
 e2e     same metric through the C ABI with HOST buffers (roadsurf_run_host_soa): pinned host
-        records -> H2D -> kernel -> D2H of the hourly outputs, all inside the timed region.
---impl reference  the reference's CPU path: the C++ restatement of the Fortran loop (oracle/,
-        compiled with the reference's own -Ofast flag set; no Fortran compiler exists here, see
-        DESIGN.md) on all host cores, on a bounded sample of the same workload.
+        records -> H2D -> kernel -> D2H of the hourly outputs, all inside the timed region; the grid's
+        horizon table is resident on the device (roadsurf_prepare_statics), as for repeated forecasts.
+--impl reference  the reference's CPU path: the C++ restatement of the Fortran loop (oracle/, compiled with
+        the reference's own -Ofast flag set; oracle/_ref -- the gfortran build -- is used instead when
+        it exists) on all host cores, on the first 10240 points of the very workload the GPU arm runs.
+--inproc  one process drives all N GPUs through the library's own `ngpus` argument
+        (roadsurf_run_host_soa(..., ngpus=N)) and compares the result with the one-GPU run.
 """
 import argparse
 import json
@@ -29,10 +41,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-POINTS_PER_GPU = 1_250_000
-HOURS = 24
 METRIC = "road_point_timesteps_per_sec"
 UNIT = "point-steps/s"
+CPU_SAMPLE = 10240
+
+WORKLOADS = {
+    "c4": dict(total=10_000_000, per_gpu=1_250_000, hours=24, analysis=0, coupling=False,
+               name="c4: synthetic km-scale road grid, 24 h forecast, 10^7 points over 8 GPUs"),
+    "c3": dict(total=100_000, per_gpu=100_000, hours=48, analysis=6, coupling=True,
+               name="c3: synthetic national road network, 10^5 points, 6 h analysis + 48 h forecast, coupling + relaxation"),
+    "c5": dict(total=51_000_000, per_gpu=6_375_000, hours=48, analysis=0, coupling=False,
+               name="c5: 51-member ensemble x 10^6 points (flattened member x point), 48 h forecast"),
+}
 
 
 def parse_args():
@@ -41,23 +61,37 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
-    ap.add_argument("--points-per-gpu", type=int, default=POINTS_PER_GPU)
-    ap.add_argument("--hours", type=int, default=HOURS)
-    ap.add_argument("--cpu-sample-points", type=int, default=0, help="0 = 1024 per host core, <= 8192")
+    ap.add_argument("--workload", default="c4", choices=tuple(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=("weak", "strong"))
+    ap.add_argument("--inproc", action="store_true")
+    ap.add_argument("--points-per-gpu", type=int, default=0, help="override the per-GPU point count")
+    ap.add_argument("--hours", type=int, default=0, help="override the forecast length")
+    ap.add_argument("--cpu-sample-points", type=int, default=CPU_SAMPLE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full-config", action="store_true")
     return ap.parse_args()
 
 
-def workload_config(args, extra=None):
-    cfg = {"workload": "c4 shard: synthetic km-scale road grid, 24 h forecast, 10^7/8 points per GPU",
-           "points_per_gpu": args.points_per_gpu, "sim_len": 1 + args.hours * 120, "dt_s": 30.0,
-           "nlayers": 15, "forcing": "hourly records, device-side linear interpolation",
-           "output": "every 120th step (hourly)", "sky_view_fraction": 0.3,
-           "coupling": False, "relaxation": False,
+def rank_points(args, world):
+    w = WORKLOADS[args.workload]
+    if args.points_per_gpu:
+        return args.points_per_gpu
+    if args.scaling == "strong":
+        return (w["total"] + world - 1) // world
+    return w["per_gpu"]
+
+
+def workload_config(args, world, extra=None):
+    w = WORKLOADS[args.workload]
+    hours = args.hours or w["hours"]
+    cfg = {"workload": w["name"], "scaling_mode": args.scaling, "points_per_gpu": rank_points(args, world),
+           "sim_len": 1 + (w["analysis"] + hours) * 120, "dt_s": 30.0, "nlayers": 15,
+           "forcing": "hourly records, device-side linear interpolation", "output": "every 120th step (hourly)",
+           "sky_view_fraction": 0.3, "coupling": w["coupling"], "relaxation": w["coupling"],
            "point_order": "sky-view points scattered at random in the input; gathered per launch by "
                           "roadsurf_order_points (inside the timed step)",
-           "l2": "inputs+outputs per step (4.4 GB) exceed the 126 MB L2; no flush needed"}
+           "l2": "inputs + outputs of a step (GBs) exceed the 126 MB L2; no flush needed"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -96,47 +130,124 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def cpu_arm(args, rec_sample, settings_hours, steps, warmup, threads):
-    """Times the CPU restatement (reference flag set) on `threads` host threads over the sample."""
+# ----------------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------------
+class Workload:
+    """One rank's share of a named configuration: a coarse-record device batch + how to step it."""
+
+    def __init__(self, args, rank, world, device):
+        import torch
+        from roadsurf_b200 import abi, lib, synth, synth_torch
+        self.torch, self.lib = torch, lib
+        w = WORKLOADS[args.workload]
+        self.name, self.args = args.workload, args
+        self.P = rank_points(args, world)
+        self.hours = args.hours or w["hours"]
+        self.analysis = w["analysis"]
+        self.sim_len = 1 + (self.analysis + self.hours) * 120
+        self.coupled = w["coupling"]
+        self.seed = 20191206 + rank
+        nrec = self.analysis + self.hours + 2
+        if self.coupled:
+            self.settings = abi.default_settings(self.sim_len)
+            self.settings.use_coupling = self.settings.use_relaxation = 1
+        else:
+            self.settings = abi.default_settings(self.sim_len)
+        self.params = abi.default_parameters(30.0)
+        lib.set_model(self.settings, self.params)
+        self.db = lib.DeviceBatch(self.P, self.sim_len, n_records=nrec, coarse=True, horizons=True, out_stride=120,
+                                  coupling=self.coupled, state=self.coupled)
+        start = synth.FORECAST_START - __import__("datetime").timedelta(hours=self.analysis)
+        synth_torch.fill_device_batch_chunked(self.db, seed=self.seed, start=start)
+        self.window_end = 0
+        if self.coupled:
+            self._derive_coupled()
+
+    def _derive_coupled(self):
+        """What read_input derives per point (relaxation targets, coupling index / observation), computed by
+        the library from the hourly records; observations = air temperature - 1 + noise during the analysis."""
+        torch, lib, db = self.torch, self.lib, self.db
+        g = torch.Generator(device=db.forcing.device)
+        g.manual_seed(self.seed + 77)
+        obs = db.forcing[:, lib.F_NAMES.index("tair")] - 1.0 + 0.5 * torch.randn(db.forcing.shape[0], db.ld, generator=g,
+                                                                               dtype=torch.float64, device=db.forcing.device)
+        obs[self.analysis + 1:] = -9999.9
+        db.forcing[:, lib.F_NAMES.index("TSurfObs")] = obs
+        forcing = db.forcing[:, :, :self.P].cpu().contiguous()
+        local = db.local[:, :self.P].cpu().contiguous()
+        forecast_step = self.analysis * 120
+        latest = __import__("numpy").full(self.P, forecast_step + 1, dtype="int32")
+        self.window_end = lib.read_input_derive_records(forcing, db.record_step.cpu(), self.settings, forecast_step, local,
+                                                        latest_obs_index=latest)
+        db.local[:, :self.P] = local.to(db.local.device)
+        db.coupling_window_end = self.window_end
+
+    def step(self, stream):
+        # one pass: the library gathers the sky-view points at one end of the launch (the permutation is
+        # rebuilt every step here, as a caller with changing statics would; it is static per grid)
+        self.db.build_order(stream)
+        self.db.run(stream)
+
+    def host_buffers(self):
+        torch, lib, db, P = self.torch, self.lib, self.db, self.P
+        pin = dict(pin_memory=True)
+        h = {"forcing": torch.empty((db.n_records, db.nvar, P), dtype=torch.float64, **pin),
+             "local": torch.empty((lib.L_NLOCAL, P), dtype=torch.float64, **pin),
+             "horizons": torch.empty((360, P), dtype=torch.float64, **pin),
+             "out": torch.empty((lib.O_NVAR, db.n_out, P), dtype=torch.float64, **pin),
+             "status": torch.empty(P, dtype=torch.int32, **pin)}
+        h["forcing"].copy_(db.forcing[:, :, :P])
+        h["local"].copy_(db.local[:, :P])
+        h["horizons"].copy_(db.horizons[:, :P])
+        h["tf"], h["rs"] = db.time_fields.cpu(), db.record_step.cpu()
+        return h
+
+    def cpu_case(self, npts):
+        """The first `npts` points of this rank's workload in the reference's host layout."""
+        from roadsurf_b200 import synth, synth_torch
+        rec = synth_torch.records_sample(self.db, npts)
+        arrays, settings, params = synth.case_from_records(rec, self.hours, self.analysis, int(self.coupled),
+                                                           int(self.coupled))
+        return arrays, settings, params
+
+
+def cpu_arm(arrays, settings, params, steps, warmup, threads, fast=True, backend="port"):
+    """Times the CPU implementation on `threads` host threads over the sample; returns rate + last outputs."""
     from oracle import pyoracle
-    from roadsurf_b200 import synth
-    arrays, settings, params = synth.case_from_records(rec_sample, settings_hours)
     n = arrays.npoints * arrays.sim_len
-    times = []
+    times, work, status = [], None, None
     for it in range(warmup + steps):
         work = arrays.copy()          # the reference mutates its inputs in place
         t0 = time.perf_counter()
-        pyoracle.run_batch(work, settings, params, nthreads=threads, fast=True)
+        status, _ = pyoracle.run_batch(work, settings, params, nthreads=threads, fast=fast, backend=backend)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     total = sum(times)
-    return {"value": n * len(times) / total, "seconds": total, "points": arrays.npoints,
-            "sim_len": arrays.sim_len, "ms_per_step": 1e3 * total / len(times)}
+    return {"value": n * len(times) / total, "seconds": total, "points": arrays.npoints, "sim_len": arrays.sim_len,
+            "ms_per_step": 1e3 * total / len(times)}, work, status
 
 
-def first_points(rec, npts):
-    """The first `npts` points of a record sample."""
-    from roadsurf_b200 import synth
-    sub = synth.Records(npts, rec.nrec)
-    for v in synth.RECORD_VARS:
-        setattr(sub, v, getattr(rec, v)[:npts].copy())
-    sub.lat, sub.lon, sub.sky_view = rec.lat[:npts], rec.lon[:npts], rec.sky_view[:npts]
-    sub.horizons, sub.record_step = rec.horizons[:npts], rec.record_step
-    return sub
+def reference_backend():
+    """("ref", "reference") when oracle/_ref (the gfortran build of the unmodified reference) exists, else
+    ("port", "port") with the reason."""
+    from oracle import pyoracle
+    try:
+        pyoracle.load_ref()
+        return "ref", "reference", "oracle/_ref/libroadsurf_ref.so (gfortran build of the unmodified reference)"
+    except pyoracle.ReferenceUnavailable as e:
+        return "port", "port", ("C++ restatement of the Fortran path built with the reference's -Ofast flag set; "
+                                f"the gfortran binary cannot be built here ({e})")
 
 
-def flops_per_point_step(rec_sample, hours, npts=8):
+def flops_per_point_step(arrays, settings, params, npts=8):
     """Exact arithmetic-operation count of the reference algorithm on this workload (counting
     scalar in the oracle): each add/mul/div/sqrt/exp/log/trig/pow = 1 flop."""
     from oracle import pyoracle
-    from roadsurf_b200 import synth
-    import numpy as np
-    sub = first_points(rec_sample, npts)
-    arrays, settings, params = synth.case_from_records(sub, hours)
     tot, steps = {}, 0
-    for p in range(npts):
-        c, s = pyoracle.count_ops(arrays, settings, params, p)
+    for p in range(min(npts, arrays.npoints)):
+        c, s = pyoracle.count_ops(arrays.copy(), settings, params, p)
         steps += s
         for k, v in c.items():
             tot[k] = tot.get(k, 0) + v
@@ -146,26 +257,97 @@ def flops_per_point_step(rec_sample, hours, npts=8):
 
 
 def run_reference(args):
-    """The reference's CPU implementation of the path on the box's host cores (rank 0 only)."""
+    """The reference's CPU implementation of the path on the box's host cores (rank 0 only), on the first
+    10240 points of the workload the GPU arm runs (drawn by the same generator call; the GPU, when there
+    is one, is used for the data generation only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    from roadsurf_b200 import synth
+    import torch
     cores = os.cpu_count() or 1
-    npts = args.cpu_sample_points or min(8192, 1024 * cores)
-    rec = synth.draw_records(npts, args.hours + 2, 20191206, synth.FORECAST_START)
-    rec.TSurfObs[:, :] = -9999.9
-    r = cpu_arm(args, rec, args.hours, args.steps, args.warmup, cores)
-    sample = f"{npts} points x {r['sim_len']} steps per step (same generator and shape as the GPU workload)"
+    npts = args.cpu_sample_points
+    world = max(1, args.gpus)
+    if torch.cuda.is_available():
+        from roadsurf_b200 import build as rs_build
+        rs_build.build_library()
+        torch.cuda.set_device(0)
+        wl = Workload(args, 0, world, torch.device("cuda", 0))
+        arrays, settings, params = wl.cpu_case(npts)
+        source = "the first %d points of the GPU arm's rank-0 workload (same generator call, same seed)" % arrays.npoints
+        del wl
+        torch.cuda.empty_cache()
+    else:
+        from roadsurf_b200 import synth
+        w = WORKLOADS[args.workload]
+        hours = args.hours or w["hours"]
+        arrays, settings, params, _ = synth.make_case(npts, hours, 20191206, analysis_hours=w["analysis"],
+                                                      use_coupling=int(w["coupling"]), use_relaxation=int(w["coupling"]),
+                                                      obs_bias=False)
+        source = "%d points of the same shape from the numpy generator (no GPU in this process)" % npts
+    backend, kind, note = reference_backend()
+    r, _, _ = cpu_arm(arrays, settings, params, args.steps, args.warmup, cores, fast=True, backend=backend)
+    sample = f"{r['points']} points x {r['sim_len']} steps per step: {source}"
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(args),
-            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "note": "C++ restatement of the Fortran path built with the reference's -Ofast "
-                                     "flag set; the gfortran binary cannot be built here (no Fortran compiler)"},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, world),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "note": note},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def kernel_traffic_per_point_step():
+    """DRAM traffic of the step kernel per point-step from the committed ncu capture (profiles/*.json)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")))
+        return float(d["dram_bytes_per_point_step"]), d.get("source", "profiles/r02_kernel_traffic.json")
+    except Exception:
+        return None, None
+
+
+def run_inproc(args):
+    """One process, N GPUs through the product's own `ngpus` argument; compared with the 1-GPU result."""
+    import torch
+    from roadsurf_b200 import build as rs_build, lib
+    rs_build.build_library()
+    lib.load()
+    n = max(1, args.gpus)
+    torch.cuda.set_device(0)
+    one = Workload(args, 0, 1, torch.device("cuda", 0))          # one shard's data ...
+    P, total = one.P, one.P * n
+    hb = one.host_buffers()
+    rep = lambda t: t.repeat(*([1] * (t.dim() - 1)), n).contiguous().pin_memory()   # ... tiled N times along the points
+    forcing, local, hor = rep(hb["forcing"]), rep(hb["local"]), rep(hb["horizons"])
+    out = torch.empty((lib.O_NVAR, one.db.n_out, total), dtype=torch.float64).pin_memory()
+    status = torch.empty(total, dtype=torch.int32).pin_memory()
+
+    def call(ngpus, o, st, sl=slice(None), statics=None):
+        lib.run_host_soa(one.settings, one.params, forcing[:, :, sl].contiguous() if sl != slice(None) else forcing, hb["tf"],
+                         local[:, sl].contiguous() if sl != slice(None) else local, o, record_step=hb["rs"],
+                         horizons=(hor[:, sl].contiguous() if sl != slice(None) else hor) if statics is None else None,
+                         status=st, out_stride=120, ngpus=ngpus, coupling_window_end=one.window_end, statics=statics)
+    ref_out = torch.empty((lib.O_NVAR, one.db.n_out, P), dtype=torch.float64)
+    ref_status = torch.empty(P, dtype=torch.int32)
+    call(1, ref_out, ref_status, slice(0, P))
+    handle = lib.prepare_statics(local, hor, ngpus=n)
+    for _ in range(max(1, args.warmup)):
+        call(n, out, status, statics=handle)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        call(n, out, status, statics=handle)
+    dt = time.perf_counter() - t0
+    st = lib.last_batch_stats()
+    same = all(bool(torch.equal(out[:, :, k * P:(k + 1) * P], ref_out)) and bool(torch.equal(status[k * P:(k + 1) * P], ref_status))
+               for k in range(n))
+    lib.release_statics(handle)
+    v = total * one.sim_len * args.steps / dt
+    line = {"impl": "ours-inproc", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": n, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, n, {"api": f"one process, roadsurf_run_host_soa(..., ngpus={n}) over pinned host "
+                                                       "buffers; points [g*P/G,(g+1)*P/G) per GPU, one host thread per GPU"}),
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"])},
+            "shards_bit_identical_to_one_gpu_run": same, "gpu_launches": int(st["kernel_launches"]) * args.steps}
     print(json.dumps(line), flush=True)
 
 
@@ -174,11 +356,15 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.inproc:
+        run_inproc(args)
+        return
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     from roadsurf_b200 import build as rs_build
-    from roadsurf_b200 import abi, lib, sharding, synth, synth_torch
+    from roadsurf_b200 import lib, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,26 +378,15 @@ def main():
     if rank == 0:
         rs_build.build_library()
     sharding.barrier(dev)
-    handle = lib.load()
+    lib.load()
     launches0 = lib.last_launch()["launches_total"]
 
-    P, hours = args.points_per_gpu, args.hours
-    sim_len = 1 + hours * 120
-    settings = abi.default_settings(sim_len)
-    params = abi.default_parameters(30.0)
-    lib.set_model(settings, params)
-    db = lib.DeviceBatch(P, sim_len, n_records=hours + 2, coarse=True, horizons=True, out_stride=120)
-    synth_torch.fill_device_batch(db, seed=20191206 + rank)
+    wl = Workload(args, rank, world, dev)
+    db, P, sim_len = wl.db, wl.P, wl.sim_len
     stream = torch.cuda.current_stream()
 
-    def step():
-        # one pass: the library gathers the sky-view points at one end of the launch (the permutation is
-        # rebuilt every step here, as a caller with changing statics would; it is static per grid)
-        db.build_order(stream)
-        db.run(stream)
-
     for _ in range(max(args.warmup, 0)):
-        step()
+        wl.step(stream)
     torch.cuda.synchronize()
     sharding.barrier(dev)
     sampler = ClockSampler(local_rank)
@@ -220,40 +395,36 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     launches_before = lib.last_launch()["launches_total"] if args.warmup > 0 else launches0
+    db.counters.zero_()
     e0.record(stream)
     for _ in range(args.steps):
-        step()
+        wl.step(stream)
     e1.record(stream)
     torch.cuda.synchronize()
     sharding.barrier(dev)
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    kernel_ms = ms_total / args.steps                      # one step kernel launch (+ the order kernel) per step
+    kernel_ms = ms_total / args.steps
     ms_max = sharding.reduce_over_ranks(ms_total, "max", dev)
     total_points = sharding.reduce_over_ranks(P, "sum", dev)
     value = total_points * sim_len * args.steps / (ms_max * 1e-3)
     cnt = db.counters.cpu().numpy()
-    failed_points = int(cnt[lib.CNT_FAILED_POINTS])
+    failed_points = int(cnt[lib.CNT_FAILED_POINTS]) // max(1, args.steps)
+    executed_over_nominal = float(cnt[lib.CNT_EXECUTED_STEPS]) / (float(P) * sim_len * args.steps)
     bl_per_step = float(cnt[lib.CNT_BL_ITERATIONS]) / max(1.0, float(cnt[lib.CNT_EXECUTED_STEPS]))
     launch = lib.last_launch()
-    gpu_launches = launch["launches_total"] - launches_before   # per step: order kernel, solar table, step kernel
+    gpu_launches = launch["launches_total"] - launches_before
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------
     e2e = None
     if not args.no_e2e:
-        pin = dict(pin_memory=True)
-        h_forcing = torch.empty((db.n_records, db.nvar, P), dtype=torch.float64, **pin)
-        h_forcing.copy_(db.forcing[:, :, :P])
-        h_local = torch.empty((lib.L_NLOCAL, P), dtype=torch.float64, **pin).copy_(db.local[:, :P])
-        h_hor = torch.empty((360, P), dtype=torch.float64, **pin).copy_(db.horizons[:, :P])
-        h_tf = db.time_fields.cpu()
-        h_rs = db.record_step.cpu()
-        h_out = torch.empty((lib.O_NVAR, db.n_out, P), dtype=torch.float64, **pin)
-        h_status = torch.empty(P, dtype=torch.int32, **pin)
+        h = wl.host_buffers()
+        statics = lib.prepare_statics(h["local"], h["horizons"], ngpus=1)
 
         def one():
-            lib.run_host_soa(settings, params, h_forcing, h_tf, h_local, h_out, record_step=h_rs,
-                             horizons=h_hor, status=h_status, out_stride=120, ngpus=1)
+            lib.run_host_soa(wl.settings, wl.params, h["forcing"], h["tf"], h["local"], h["out"], record_step=h["rs"],
+                             status=h["status"], out_stride=120, ngpus=1, coupling_window_end=wl.window_end,
+                             statics=statics)
         one()                                              # warm-up: sizes the device work space
         torch.cuda.synchronize()
         sharding.barrier(dev)
@@ -265,21 +436,24 @@ def main():
         sharding.barrier(dev)
         st = lib.last_batch_stats()
         t_max = sharding.reduce_over_ranks(t_e2e, "max", dev)
-        same = bool(torch.equal(h_out.to(dev), db.out[:, :, :P]))
+        same = bool(torch.equal(h["out"].to(dev), db.out[:, :, :P]))
         e2e = {"value": total_points * sim_len * args.steps / t_max, "unit": UNIT,
                "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]),
-               "ms_per_step": 1e3 * t_max / args.steps, "api": "roadsurf_run_host_soa (pinned host buffers)",
-               "breakdown_ms": {"h2d": st["h2d_ms"], "kernel": st["kernel_ms"], "d2h": st["d2h_ms"],
-                                "chunks": st["groups"]},
+               "ms_per_step": 1e3 * t_max / args.steps,
+               "api": "roadsurf_run_host_soa (pinned host buffers; horizon table resident via roadsurf_prepare_statics: "
+                      "%d bytes uploaded once, outside the timed region)" % (360 * 8 * P),
+               "breakdown_ms": {"h2d": st["h2d_ms"], "kernel": st["kernel_ms"], "d2h": st["d2h_ms"], "chunks": st["groups"]},
                "outputs_equal_device_run": same}
         gpu_launches += st["kernel_launches"] * args.steps
+        lib.release_statics(statics)
+        del h
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant (only) kernel ---------------------------------------------------
+    # ---- the binding roofline (fp64) and the HBM one ----------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -290,48 +464,109 @@ def main():
                  db.horizons[:, :P].numel()) * 8 + P * 4
     hbm_achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     fp64_peak = lib.measure_fp64_tflops(40000)
-    rec_sample = synth_torch.records_sample(db, args.cpu_sample_points or min(8192, 1024 * (os.cpu_count() or 1)))
-    flops, per = flops_per_point_step(rec_sample, hours)
+    nsample = min(args.cpu_sample_points, P)
+    arrays, s_settings, s_params = wl.cpu_case(nsample)
+    flops, per = flops_per_point_step(arrays, s_settings, s_params)
     fp64_achieved = flops * P * sim_len / (kernel_ms * 1e-3) / 1e12
-    # DRAM traffic of this kernel from the committed ncu --set full capture (profiles/r01_h_libm_exact_ncu_summary.txt:
-    # dram__bytes_read.sum + dram__bytes_write.sum = 943.6 MB for 227 328 points x 2881 steps), scaled to this launch
-    traffic = 943.588352e6 / (227328 * 2881) * P * sim_len if (P >= 151552 and hours == 24) else None
-    roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": hbm_achieved / hbm_peak, "traffic": traffic,
-                "traffic_source": "ncu capture of the same kernel variant at 227328 points, scaled by point-steps",
-                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "algorithmic_bytes_per_point_step": alg_bytes / (P * sim_len),
-                "note": "coarse-forcing mode moves ~1.2 B per point-step: this kernel is bound by the fp64 "
-                        "pipe (see roofline_fp64; ncu: fp64 pipe 54 % busy, issue slots 59 %), not by HBM"}
-    roofline_fp64 = {"bound": "fp64", "achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": fp64_achieved / fp64_peak,
-                     "peak_source": "DFMA micro-benchmark run live by this script (FMA = 2 flop)",
-                     "algorithmic_flops_per_point_step": flops, "ops_per_point_step": per,
-                     "note": "algorithmic flops count div/sqrt/exp/log/trig as 1 each; in issued fp64 "
-                             "instructions they cost ~10-40, see profiles/ for the pipe utilisation"}
+    traffic_pps, traffic_src = kernel_traffic_per_point_step()
+    traffic = traffic_pps * P * sim_len if (traffic_pps and args.workload == "c4") else None
+    roofline = {"bound": "fp64", "achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": fp64_achieved / fp64_peak,
+                "peak_source": "DFMA micro-benchmark run live by this script (FMA = 2 flop); MEASURED_PEAKS.json has no fp64 figure",
+                "algorithmic_flops_per_point_step": flops, "ops_per_point_step": per,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "pipe_utilisation": "ncu: fp64 pipe 66.5 % busy, issue slots 66.5 % (profiles/r02_c_cold_outline_ncu_summary.txt)",
+                "note": "algorithmic flops count div/sqrt/exp/log/trig as 1 each; in issued fp64 instructions they cost "
+                        "~10-40, so the pipe utilisation (ncu) is the fairer reading of how full the machine is"}
+    roofline_hbm = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm_achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "algorithmic_bytes_per_point_step": alg_bytes / (P * sim_len),
+                    "note": "coarse-forcing mode moves ~2 B per point-step: HBM is not the binding ceiling of this kernel"}
 
-    cpu_baseline = None
+    # ---- CPU baseline + parity of the benchmarked workload itself ---------------------------------
+    cpu_baseline, parity_sample = None, None
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        r = cpu_arm(args, rec_sample, hours, 1, 0, cores)
-        r1 = cpu_arm(args, first_points(rec_sample, min(512, rec_sample.npoints)), hours, 1, 0, 1)
-        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
-                        "one_core_value": r1["value"],
+        backend, kind, note = reference_backend()
+        r, _, _ = cpu_arm(arrays, s_settings, s_params, 1, 0, cores, fast=True, backend=backend)
+        sub = arrays.copy()
+        r1, _, _ = cpu_arm(_first(sub, 512), s_settings, s_params, 1, 0, 1, fast=True, backend=backend)
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": kind, "one_core_value": r1["value"],
                         "sample": f"first {r['points']} points of the GPU workload x {r['sim_len']} steps, "
-                                  f"{r['seconds']:.1f} s wall on {cores} threads",
-                        "note": "C++ restatement of the Fortran path, reference -Ofast flag set (no gfortran here)"}
+                                  f"{r['seconds']:.1f} s wall on {cores} threads", "note": note}
+        # the parity oracle (strict build) on the same points against what the GPU produced in the timed run
+        _, work, st_cpu = cpu_arm(arrays, s_settings, s_params, 1, 0, cores, fast=False)
+        o = db.out[:, :, :nsample].cpu().numpy()
+        names = lib.O_NAMES
+        identical = all(np.array_equal(np.ascontiguousarray(o[v].T), work.out[name][:, ::120], equal_nan=True)
+                        for v, name in enumerate(names))
+        st_gpu = db.status[:nsample].cpu().numpy()
+        parity_sample = {"points": int(nsample), "steps_compared": int(o.shape[1]), "bit_identical": bool(identical),
+                         "status_words_equal": bool(np.array_equal(st_gpu, st_cpu)),
+                         "oracle": "oracle/ strict build (parity unpinned: never compared with a gfortran build)"}
+
+    # ---- the full named configuration on ONE GPU (c4: 10^7 points fit) ----------------------------
+    full_config = None
+    if (args.workload == "c4" and args.scaling == "weak" and world == 1 and not args.no_full_config
+            and not args.points_per_gpu and not args.hours):
+        del wl, db
+        torch.cuda.empty_cache()
+        full_config = run_full_c4(args, dev)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, {"kernel_regs": launch["regs_per_thread"], "grid": launch["grid"],
-                                             "block": launch["block"], "bl_iterations_per_step": bl_per_step,
-                                             "failed_points": failed_points}),
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world, {"kernel_regs": launch["regs_per_thread"], "grid": launch["grid"],
+                                                    "block": launch["block"], "bl_iterations_per_step": bl_per_step,
+                                                    "failed_points": failed_points,
+                                                    "executed_over_nominal_steps": executed_over_nominal}),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
-            "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu_baseline}
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
+            "parity_sample": parity_sample, "full_config": full_config}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _first(arrays, n):
+    """The first n points of a PointArrays (views copied)."""
+    from roadsurf_b200 import abi
+    import ctypes as C
+    n = min(n, arrays.npoints)
+    sub = abi.PointArrays(n, arrays.sim_len)
+    for name in [f[2:] for f in abi.INPUT_DOUBLE_FIELDS] + ["PrecPhase", "local_horizons", "Depth"]:
+        getattr(sub, name)[...] = getattr(arrays, name)[:n]
+    sub.time[...] = arrays.time
+    C.memmove(sub.local, arrays.local, C.sizeof(abi.LocalParameters) * n)
+    return sub
+
+
+def run_full_c4(args, dev):
+    """BASELINE config 4 in full on one B200: 10^7 points x 2881 steps, one launch (65 GB resident)."""
+    import torch
+    from roadsurf_b200 import abi, lib, synth_torch
+    P, hours = WORKLOADS["c4"]["total"], WORKLOADS["c4"]["hours"]
+    sim_len = 1 + hours * 120
+    lib.set_model(abi.default_settings(sim_len), abi.default_parameters(30.0))
+    db = lib.DeviceBatch(P, sim_len, n_records=hours + 2, coarse=True, horizons=True, out_stride=120)
+    synth_torch.fill_device_batch_chunked(db, seed=20191206)
+    st = torch.cuda.current_stream()
+    db.build_order(st)
+    db.run(st)                                              # warm-up pass
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    db.build_order(st)
+    db.run(st)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    cnt = db.counters.cpu().numpy()
+    return {"workload": "c4 in full on one GPU: 10^7 points x 2881 steps, single launch", "points": P, "ms_per_step": ms,
+            "value": P * sim_len / (ms * 1e-3), "unit": UNIT, "steps": 1, "warmup": 1,
+            "hbm_resident_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
+            "failed_points": int(cnt[lib.CNT_FAILED_POINTS]) // 2, "grid": lib.last_launch()["grid"]}
 
 
 if __name__ == "__main__":

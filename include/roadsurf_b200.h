@@ -390,12 +390,26 @@ typedef struct RsHostBatch
   int* status;                /* [npoints] or NULL */
   int coupling_window_end;    /* as in RsDeviceBatch: 0, or the couplingIndexI every coupled point has
                                  (enables lane compaction between coupling iterations) */
+  void* statics;              /* NULL, or a handle from roadsurf_prepare_statics for this grid of points:
+                                 the local horizon table (and the point order derived from the sky-view
+                                 factors) is then already on the device(s) and `horizons` is not read */
 } RsHostBatch;
 
 /* Runs a host SoA batch on `ngpus` devices (<= 0: all visible; 1: the current device), points
  * split into contiguous shards.  Synchronous.  Statistics via roadsurf_last_batch_stats. */
 int roadsurf_run_host_soa(const RsHostBatch* batch, const InputSettings* settings,
                           const InputParameters* params, int ngpus);
+
+/* Repeated forecasts over ONE grid of points: the per-point statics that do not change between
+ * forecasts -- the 360-entry local horizon table (2880 of the ~5250 bytes a config-4 point uploads per
+ * call) and the point order that gathers the sky-view points -- are uploaded once and kept on the
+ * device(s).  `batch` supplies npoints, local (only the sky-view plane is read) and horizons, all with
+ * the layout of roadsurf_run_host_soa; `ngpus` must be the value later passed to roadsurf_run_host_soa.
+ * The handle goes into RsHostBatch.statics of every later call for the same grid; the per-forecast
+ * planes of `local` (relaxation targets, coupling observation / index, InitLenI) are still taken from
+ * each call's batch.  Returns RS_OK or an error; release with roadsurf_release_statics. */
+int roadsurf_prepare_statics(const RsHostBatch* batch, int ngpus, void** handle);
+void roadsurf_release_statics(void* handle);
 
 /* roadsurf_read_input_derive for a batch held as coarse records (forcing_mode 1): what read_input
  * would derive from the time-interpolated arrays (examples/example1/src/roadrunner.cpp:157-278 after

@@ -767,6 +767,58 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
   }
   return RS_OK;
 }
+// Column chunks of a host-SoA shard: a multiple of 32 points, about 1/8 of the shard but at least 64 Ki points.
+int host_soa_chunk(int count)
+{
+  int chunk = ((count + 7) / 8 + 31) / 32 * 32;
+  if (chunk < 65536) chunk = std::min((count + 31) / 32 * 32, 65536);
+  return chunk;
+}
+
+// roadsurf_prepare_statics: per device shard and per chunk of roadsurf_run_host_soa's pipeline, the local
+// horizon table [360][ld] and the sky-view point order [ld], resident on the device.
+struct StaticsChunk
+{
+  double* hor = nullptr;  // [360][ld] or null (no horizons given)
+  int* order = nullptr;   // [ld]
+  int ld = 0;
+};
+struct StaticsShard
+{
+  int device = 0, first = 0, count = 0, chunk = 0;
+  std::vector<StaticsChunk> chunks;
+};
+struct RsStatics
+{
+  unsigned magic = 0x52535354u;  // "RSST"
+  int npoints = 0, ngpus = 0;
+  bool has_horizons = false;
+  std::vector<StaticsShard> shards;
+};
+
+// Streams and events of the host-SoA pipeline, created once per device and reused by every call (the
+// calls of one device are serialised by g_device_mu).
+struct SoaStreams
+{
+  cudaStream_t st[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2][4] = {};
+};
+std::mutex g_soa_mu;
+std::map<int, SoaStreams> g_soa_streams;
+int soa_streams(int device, SoaStreams** out)
+{
+  std::lock_guard<std::mutex> lk(g_soa_mu);
+  SoaStreams& s = g_soa_streams[device];
+  if (!s.st[0])
+    for (int k = 0; k < 2; ++k)
+    {
+      CU(cudaStreamCreateWithFlags(&s.st[k], cudaStreamNonBlocking));
+      for (int e = 0; e < 4; ++e) CU(cudaEventCreate(&s.ev[k][e]));
+    }
+  *out = &s;
+  return RS_OK;
+}
+
 // Points [first, first+count) of a host SoA batch on `device`, pipelined in column chunks over two
 // streams: H2D(chunk c+1) overlaps kernel(chunk c) overlaps D2H(chunk c-1).
 int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* settings,
@@ -783,34 +835,31 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
   const int n_out = (b->sim_len + b->out_stride - 1) / b->out_stride;
   const size_t np_all = static_cast<size_t>(b->npoints);
   constexpr int NSTREAM = 2;
-  // chunk size: a multiple of 32 points, about 1/8 of the shard but at least 64 Ki points
-  int chunk = ((sh.count + 7) / 8 + 31) / 32 * 32;
-  if (chunk < 65536) chunk = std::min((sh.count + 31) / 32 * 32, 65536);
+  const int chunk = host_soa_chunk(sh.count);
   const int nchunks = (sh.count + chunk - 1) / chunk;
   const size_t frows = static_cast<size_t>(b->n_records) * b->nvar;
   const size_t orows = static_cast<size_t>(RS_O_NVAR) * n_out;
-  const bool hor = b->horizons != nullptr;
-
-  cudaStream_t streams[NSTREAM];
-  cudaEvent_t ev[NSTREAM][4];
-  for (int s = 0; s < NSTREAM; ++s)
+  // statics resident on the device (roadsurf_prepare_statics)?
+  const StaticsShard* resident = nullptr;
+  if (b->statics)
   {
-    CU(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
-    for (int k = 0; k < 4; ++k) CU(cudaEventCreate(&ev[s][k]));
+    const RsStatics* h = static_cast<const RsStatics*>(b->statics);
+    if (h->magic != 0x52535354u || h->npoints != b->npoints)
+      return fail(RS_ERR_BAD_ARGUMENT, "statics handle does not belong to a grid of this many points");
+    for (const StaticsShard& s : h->shards)
+      if (s.device == sh.device && s.first == sh.first && s.count == sh.count && s.chunk == chunk) resident = &s;
+    if (!resident || static_cast<int>(resident->chunks.size()) != nchunks)
+      return fail(RS_ERR_BAD_ARGUMENT, "statics handle was prepared for another ngpus / device set");
   }
-  struct Guard
+  const bool hor = resident ? resident->chunks[0].hor != nullptr : b->horizons != nullptr;
+
+  SoaStreams* ss = nullptr;
   {
-    cudaStream_t* st;
-    cudaEvent_t (*ev)[4];
-    ~Guard()
-    {
-      for (int s = 0; s < NSTREAM; ++s)
-      {
-        for (int k = 0; k < 4; ++k) cudaEventDestroy(ev[s][k]);
-        cudaStreamDestroy(st[s]);
-      }
-    }
-  } guard{streams, ev};
+    const int rc = soa_streams(sh.device, &ss);
+    if (rc != RS_OK) return rc;
+  }
+  cudaStream_t* streams = ss->st;
+  cudaEvent_t(*ev)[4] = ss->ev;
 
   // per-stream device buffers
   double *d_forcing[NSTREAM], *d_out[NSTREAM], *d_local[NSTREAM], *d_hor[NSTREAM], *d_scratch[NSTREAM],
@@ -830,7 +879,7 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     CU(pool_get(sh.device, 10 * s + 2, sizeof(double) * RS_L_NLOCAL * chunk, &tmp));
     d_local[s] = static_cast<double*>(tmp);
     d_hor[s] = nullptr;
-    if (hor)
+    if (hor && !resident)
     {
       CU(pool_get(sh.device, 10 * s + 3, sizeof(double) * 360 * chunk, &tmp));
       d_hor[s] = static_cast<double*>(tmp);
@@ -850,7 +899,7 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
       d_state[s] = static_cast<double*>(tmp);
     }
     d_order[s] = nullptr;
-    if (hor && b->forcing_mode == 1)  // sky-view points gathered at one end of the chunk (see roadsurf_order_points)
+    if (hor && !resident && b->forcing_mode == 1)  // sky-view points gathered at one end of the chunk (see roadsurf_order_points)
     {
       CU(pool_get(sh.device, 10 * s + 7, sizeof(int) * chunk, &tmp));
       d_order[s] = static_cast<int*>(tmp);
@@ -900,10 +949,10 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
                          frows, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpy2DAsync(d_local[s], sizeof(double) * ld, b->local + col0, sizeof(double) * np_all, wbytes,
                          RS_L_NLOCAL, cudaMemcpyHostToDevice, st));
-    if (hor)
+    if (hor && !resident)
       CU(cudaMemcpy2DAsync(d_hor[s], sizeof(double) * ld, b->horizons + col0, sizeof(double) * np_all, wbytes, 360,
                            cudaMemcpyHostToDevice, st));
-    sh.stats.h2d_bytes += wbytes * (frows + RS_L_NLOCAL + (hor ? 360 : 0));
+    sh.stats.h2d_bytes += wbytes * (frows + RS_L_NLOCAL + ((hor && !resident) ? 360 : 0));
     CU(cudaEventRecord(ev[s][1], st));
     RsArgs a;
     std::memset(&a, 0, sizeof a);
@@ -923,7 +972,7 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     a.record_step = d_rs;
     a.tf = d_tf;
     a.local = d_local[s];
-    a.horizons = d_hor[s];
+    a.horizons = resident ? resident->chunks[c].hor : d_hor[s];
     a.solar = d_solar;
     a.out = d_out[s];
     a.status = d_status[s];
@@ -934,7 +983,12 @@ int run_host_soa_shard(Shard& sh, const RsHostBatch* b, const InputSettings* set
     ac.out_start = 0;
     ac.out_nvar = RS_O_NVAR;
     ac.state = d_state[s];
-    if (d_order[s])
+    if (resident && b->forcing_mode == 1 && resident->chunks[c].order)
+    {
+      ac.index = resident->chunks[c].order;  // built once by roadsurf_prepare_statics
+      ac.n_fixed = ld;
+    }
+    else if (d_order[s])
     {
       CU(static_cast<cudaError_t>(rs_launch_partition(d_local[s] + static_cast<size_t>(RS_L_SKY_VIEW) * ld, ld, npc, 2,
                                                       d_order[s], nullptr, st)));
@@ -1048,6 +1102,92 @@ int roadsurf_run_host_soa(const RsHostBatch* b, const InputSettings* settings, c
     return fail(RS_ERR_BAD_ARGUMENT, "null host pointer in batch");
   if (b->npoints == 0) return roadsurf_device_count() < 1 ? fail(RS_ERR_NO_DEVICE, "no CUDA device visible") : RS_OK;
   return run_sharded(b->npoints, ngpus, [&](Shard& sh) { return run_host_soa_shard(sh, b, settings, params); });
+}
+
+int roadsurf_prepare_statics(const RsHostBatch* b, int ngpus, void** handle)
+{
+  g_err.clear();
+  if (!b || !handle || b->npoints < 1 || !b->local) return fail(RS_ERR_BAD_ARGUMENT, "bad arguments");
+  const int ndev = roadsurf_device_count();
+  if (ndev < 1) return fail(RS_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
+  if (ngpus <= 0 || ngpus > ndev) ngpus = ndev;
+  if (ngpus > b->npoints) ngpus = b->npoints;
+  int current = 0;
+  cudaGetDevice(&current);
+  RsStatics* h = new RsStatics;
+  h->npoints = b->npoints;
+  h->ngpus = ngpus;
+  h->has_horizons = b->horizons != nullptr;
+  const size_t np_all = static_cast<size_t>(b->npoints);
+  int rc = RS_OK;
+  for (int g = 0; g < ngpus && rc == RS_OK; ++g)
+  {
+    StaticsShard s;
+    s.first = static_cast<int>(static_cast<long long>(b->npoints) * g / ngpus);
+    s.count = static_cast<int>(static_cast<long long>(b->npoints) * (g + 1) / ngpus) - s.first;
+    s.device = (ngpus == 1) ? current : g;
+    s.chunk = host_soa_chunk(s.count);
+    auto body = [&]() -> int {
+      CU(cudaSetDevice(s.device));
+      for (int q0 = 0; q0 < s.count; q0 += s.chunk)
+      {
+        StaticsChunk ch;
+        const int npc = std::min(s.chunk, s.count - q0);
+        ch.ld = (npc + 31) / 32 * 32;
+        const size_t col0 = static_cast<size_t>(s.first) + q0;
+        double* d_sky = nullptr;
+        CU(cudaMalloc(&d_sky, sizeof(double) * ch.ld));
+        CU(cudaMemset(d_sky, 0, sizeof(double) * ch.ld));
+        CU(cudaMemcpy(d_sky, b->local + static_cast<size_t>(RS_L_SKY_VIEW) * np_all + col0, sizeof(double) * npc,
+                      cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&ch.order, sizeof(int) * ch.ld));
+        CU(static_cast<cudaError_t>(rs_launch_partition(d_sky, ch.ld, npc, 2, ch.order, nullptr, nullptr)));
+        ++g_launches_total;
+        if (b->horizons)
+        {
+          CU(cudaMalloc(&ch.hor, sizeof(double) * 360 * ch.ld));
+          CU(cudaMemset(ch.hor, 0, sizeof(double) * 360 * ch.ld));
+          CU(cudaMemcpy2D(ch.hor, sizeof(double) * ch.ld, b->horizons + col0, sizeof(double) * np_all,
+                          sizeof(double) * npc, 360, cudaMemcpyHostToDevice));
+        }
+        CU(cudaDeviceSynchronize());
+        cudaFree(d_sky);
+        s.chunks.push_back(ch);
+      }
+      return RS_OK;
+    };
+    rc = body();
+    h->shards.push_back(s);
+  }
+  cudaSetDevice(current);
+  if (rc != RS_OK)
+  {
+    const std::string err = g_err;
+    roadsurf_release_statics(h);
+    return fail(rc, err);
+  }
+  *handle = h;
+  return RS_OK;
+}
+
+void roadsurf_release_statics(void* handle)
+{
+  RsStatics* h = static_cast<RsStatics*>(handle);
+  if (!h || h->magic != 0x52535354u) return;
+  int current = 0;
+  cudaGetDevice(&current);
+  for (StaticsShard& s : h->shards)
+  {
+    cudaSetDevice(s.device);
+    for (StaticsChunk& ch : s.chunks)
+    {
+      if (ch.hor) cudaFree(ch.hor);
+      if (ch.order) cudaFree(ch.order);
+    }
+  }
+  cudaSetDevice(current);
+  h->magic = 0;
+  delete h;
 }
 
 const char* roadsurf_last_error(void) { return g_err.c_str(); }

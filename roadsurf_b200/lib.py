@@ -34,7 +34,7 @@ EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roa
            "roadsurf_transpose_to_soa", "roadsurf_transpose_from_soa", "roadsurf_fill",
            "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_selftest_libm", "roadsurf_runsimulation_counters", "roadsurf_order_points", "roadsurf_default_parameters",
            "roadsurf_default_settings", "roadsurf_set_option", "roadsurf_release_workspace",
-           "roadsurf_last_launch",
+           "roadsurf_last_launch", "roadsurf_prepare_statics", "roadsurf_release_statics",
            "roadsurf_version")
 
 
@@ -76,7 +76,7 @@ class RsHostBatch(C.Structure):
                 ("nvar", C.c_int), ("out_stride", C.c_int),
                 ("forcing", C.c_void_p), ("record_step", C.c_void_p), ("time_fields", C.c_void_p),
                 ("local", C.c_void_p), ("horizons", C.c_void_p), ("out", C.c_void_p), ("status", C.c_void_p),
-                ("coupling_window_end", C.c_int)]
+                ("coupling_window_end", C.c_int), ("statics", C.c_void_p)]
 
 
 class RoadSurfError(RuntimeError):
@@ -189,8 +189,31 @@ def run_batch(arrays, settings, params, ngpus=1):
     return PreparedBatch(arrays).run(settings, params, ngpus)
 
 
+def prepare_statics(local, horizons, ngpus=1):
+    """roadsurf_prepare_statics: upload the horizon table of a grid once; returns the handle to pass as
+    `statics=` to run_host_soa (release with release_statics)."""
+    def ptr(x):
+        if x is None:
+            return None
+        return x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
+    npoints = local.shape[1]
+    hb = RsHostBatch(npoints=npoints, local=ptr(local), horizons=ptr(horizons))
+    handle = C.c_void_p(None)
+    lib = load()
+    lib.roadsurf_prepare_statics.argtypes = [C.POINTER(RsHostBatch), C.c_int, C.POINTER(C.c_void_p)]
+    _check(lib.roadsurf_prepare_statics(C.byref(hb), int(ngpus), C.byref(handle)))
+    return handle
+
+
+def release_statics(handle):
+    lib = load()
+    lib.roadsurf_release_statics.argtypes = [C.c_void_p]
+    lib.roadsurf_release_statics.restype = None
+    lib.roadsurf_release_statics(handle)
+
+
 def run_host_soa(settings, params, forcing, time_fields, local, out, record_step=None, horizons=None,
-                 status=None, out_stride=1, ngpus=1, coupling_window_end=0):
+                 status=None, out_stride=1, ngpus=1, coupling_window_end=0, statics=None):
     """roadsurf_run_host_soa on host tensors/arrays (torch CPU tensors -- ideally pinned -- or numpy):
     forcing [n_records, nvar, npoints] f64, time_fields [6, sim_len] i32, local [L_NLOCAL, npoints],
     out [6, n_out, npoints] (written), record_step [n_records] i32 for coarse forcing."""
@@ -206,7 +229,7 @@ def run_host_soa(settings, params, forcing, time_fields, local, out, record_step
                      n_records=n_records, nvar=nvar, out_stride=out_stride, forcing=ptr(forcing),
                      record_step=ptr(record_step), time_fields=ptr(time_fields), local=ptr(local),
                      horizons=ptr(horizons), out=ptr(out), status=ptr(status),
-                     coupling_window_end=int(coupling_window_end))
+                     coupling_window_end=int(coupling_window_end), statics=statics)
     _check(load().roadsurf_run_host_soa(C.byref(hb), C.byref(settings), C.byref(params), int(ngpus)))
 
 

@@ -99,6 +99,29 @@ def fill_device_batch(db, seed, start=None, dt_secs=30.0, record_secs=3600, sky_
     return db
 
 
+def fill_device_batch_chunked(db, seed, start=None, chunk=1_250_000, **kw):
+    """fill_device_batch for batches of any size with bounded temporaries: the batch is drawn in pieces of
+    `chunk` points (piece k with seed + 1000 k, so the first piece of a large batch equals the batch of
+    `chunk` points drawn with `seed`)."""
+    if db.ld <= chunk:
+        return fill_device_batch(db, seed, start, **kw)
+    for k, p0 in enumerate(range(0, db.npoints, chunk)):
+        n = min(chunk, db.npoints - p0)
+        tmp = _lib.DeviceBatch(n, db.sim_len, nlayers=db.nlayers, n_records=db.n_records, nvar=db.nvar, coarse=True,
+                               horizons=db.horizons is not None, out_stride=db.sim_len)
+        fill_device_batch(tmp, seed + 1000 * k, start, **kw)
+        db.forcing[:, :, p0:p0 + n] = tmp.forcing[:, :, :n]
+        db.local[:, p0:p0 + n] = tmp.local[:, :n]
+        if db.horizons is not None:
+            db.horizons[:, p0:p0 + n] = tmp.horizons[:, :n]
+        db.record_step.copy_(tmp.record_step)
+        db.time_fields.copy_(tmp.time_fields)
+        del tmp
+    db.local[_lib.L_ACTIVE, db.npoints:] = 0.0
+    db.local[_lib.L_SKY_VIEW, db.npoints:] = 1.0
+    return db
+
+
 def records_sample(db, count):
     """The first `count` points of a coarse DeviceBatch as a synth.Records (numpy), for the CPU arm."""
     count = min(int(count), db.npoints)
