@@ -424,6 +424,36 @@ void roadsurf_release_statics(void* handle);
 int roadsurf_read_input_derive_records(const RsHostBatch* batch, const InputSettings* settings, int forecast_step,
                                        const int* latest_obs_index, double* local, int* window_end);
 
+/* ---- step-granular sessions (the Fortran subroutine API of module RoadSurf forwards to these) -------- */
+
+/* The library's Fortran API (src/RoadSurf.f90:9-252) advances ONE point ONE step per call sequence
+ * (CheckValues ... SaveOutput, CheckEndCoupling; examples/example1/src/Simulation.f90:58-94).  A session
+ * holds the same run on the device: inputs uploaded once, per-point state resident between launches
+ * (the resumable state planes), one call per model step.
+ *
+ * roadsurf_session_open   same arguments as roadsurf_run_batch (npoints >= 1; all points must share one
+ *                         time axis and, if coupled, one coupling window).  Pre-fills the caller's output
+ *                         arrays with -9999.0 as Initialization does (src/Initialization.f90:397-412).
+ * roadsurf_step           advance the session to model step i (1-based, <= SimLen): runs the steps
+ *                         (done, i] in one launch of the step kernel -- i = done + 1 is one launch with
+ *                         step_begin = step_end = i.  A coupling window is indivisible (its rewinds happen
+ *                         inside the kernel): a call that enters the window [start, end] runs through
+ *                         step end + 1.  i = SimLen runs the "last value" step (Simulation.f90:100-115).
+ *                         With a run-ahead chunk K > 1 (roadsurf_session_set_chunk) a call that has to
+ *                         launch anyway runs K steps at once; results are bit-identical either way.
+ * roadsurf_session_fetch  copy the outputs of every step <= i not yet delivered into the caller's output
+ *                         arrays (element i-1 <- step i), and the status words if status != NULL.
+ * roadsurf_session_done   number of steps executed so far.
+ * Results equal roadsurf_run_batch's bit for bit.  All return RS_OK or an error code. */
+int roadsurf_session_open(int npoints, OutputPointers* const* out, const InputPointers* const* in,
+                          const InputSettings* settings, const InputParameters* params,
+                          const LocalParameters* const* local, void** session);
+int roadsurf_step(void* session, int i);
+int roadsurf_session_fetch(void* session, int i, int* status);
+int roadsurf_session_set_chunk(void* session, int steps);
+int roadsurf_session_done(void* session);
+void roadsurf_session_close(void* session);
+
 /* Pack kernels for callers that hold point-major data on the device:
  * src[point][n] (row stride `src_ld` elements) -> dst plane [n][ld].  Asynchronous. */
 int roadsurf_transpose_to_soa(const double* src, int64_t src_ld, int npoints, int n, double* dst,

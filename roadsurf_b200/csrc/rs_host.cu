@@ -16,6 +16,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -1188,6 +1189,268 @@ void roadsurf_release_statics(void* handle)
   cudaSetDevice(current);
   h->magic = 0;
   delete h;
+}
+
+// ---- step-granular sessions -------------------------------------------------------------------------
+namespace
+{
+struct RsSession
+{
+  unsigned magic = 0x52535345u;  // "RSSE"
+  int device = 0, npoints = 0, ld = 0, sim_len = 0, nl = 0, nvar = 0;
+  RsModel model;
+  double *d_forcing = nullptr, *d_local = nullptr, *d_hor = nullptr, *d_out = nullptr, *d_state = nullptr,
+         *d_scratch = nullptr, *d_solar = nullptr;
+  int *d_tf = nullptr, *d_status = nullptr;
+  unsigned long long* d_counters = nullptr;
+  cudaStream_t stream = nullptr;
+  std::vector<OutputPointers> outs;
+  int done = 0, fetched = 0, chunk = 1;
+  int wstart = 0, wend = 0;  // common coupling window of the coupled points (0 = none)
+};
+RsSession* session_of(void* p)
+{
+  RsSession* s = static_cast<RsSession*>(p);
+  return (s && s->magic == 0x52535345u) ? s : nullptr;
+}
+}  // namespace
+
+int roadsurf_session_open(int npoints, OutputPointers* const* out, const InputPointers* const* in,
+                          const InputSettings* settings, const InputParameters* params,
+                          const LocalParameters* const* local, void** session)
+{
+  g_err.clear();
+  if (npoints < 1 || !out || !in || !settings || !params || !local || !session)
+    return fail(RS_ERR_BAD_ARGUMENT, "null argument");
+  if (roadsurf_device_count() < 1) return fail(RS_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
+  std::unique_ptr<RsSession, void (*)(void*)> guard(new RsSession, roadsurf_session_close);
+  RsSession* s = guard.get();
+  CU(cudaGetDevice(&s->device));
+  {
+    std::lock_guard<std::mutex> device_lock(g_device_mu[s->device & 63]);
+    const int rc = set_model_on_current_device(settings, params, &s->model);
+    if (rc != RS_OK) return rc;
+  }
+  const int sim_len = settings->SimLen, nl = s->model.nlayers;
+  s->npoints = npoints;
+  s->ld = (npoints + 31) / 32 * 32;
+  s->sim_len = sim_len;
+  s->nl = nl;
+  const size_t ld = s->ld;
+  bool any_depth = false, any_sky = false;
+  for (int p = 0; p < npoints; ++p)
+  {
+    const InputPointers* ip = in[p];
+    if (ip->inputLen < sim_len || out[p]->outputLen < sim_len)
+      return fail(RS_ERR_BAD_ARGUMENT, "inputLen/outputLen shorter than SimLen");
+    const size_t nb = sizeof(int) * sim_len;
+    const InputPointers* r = in[0];
+    if (p > 0 && (std::memcmp(r->c_year, ip->c_year, nb) || std::memcmp(r->c_month, ip->c_month, nb) ||
+                  std::memcmp(r->c_day, ip->c_day, nb) || std::memcmp(r->c_hour, ip->c_hour, nb) ||
+                  std::memcmp(r->c_minute, ip->c_minute, nb) || std::memcmp(r->c_second, ip->c_second, nb)))
+      return fail(RS_ERR_UNSUPPORTED, "the points of a session must share one time axis");
+    const LocalParameters& lp = *local[p];
+    if (lp.sky_view < 1.0 && lp.sky_view > -0.01f) any_sky = true;
+    for (int t = 0; t < sim_len && !any_depth; ++t) any_depth = ip->c_Depth[t] >= 0.0;
+    const long long w = window_key(s->model, lp);
+    if (w > 0)
+    {
+      const int cend = static_cast<int>(w);
+      const int cstart = (static_cast<double>(cend) <= s->model.coupling_span_real) ? 1 : cend - s->model.coupling_span;
+      if (s->wend && (s->wend != cend || s->wstart != cstart))
+        return fail(RS_ERR_UNSUPPORTED, "the coupled points of a session must share one coupling window");
+      s->wend = cend;
+      s->wstart = cstart;
+    }
+  }
+  const int nvar = s->nvar = any_depth ? RS_F_NVAR_DEPTH : RS_F_NVAR;
+  // ---- pack on the host: forcing [t][var][ld], statics, horizons; pre-fill the caller's outputs
+  std::vector<double> hf(static_cast<size_t>(sim_len) * nvar * ld, 0.0), hl(RS_L_NLOCAL * ld, 0.0);
+  std::vector<double> hh(any_sky ? 360 * ld : 0, 0.0);
+  s->outs.resize(npoints);
+  for (size_t q = 0; q < ld; ++q) hl[RS_L_SKY_VIEW * ld + q] = 1.0;
+  for (int p = 0; p < npoints; ++p)
+  {
+    const InputPointers* ip = in[p];
+    const double* src[RS_F_NVAR_DEPTH] = {ip->c_tair, ip->c_tdew, ip->c_VZ,     ip->c_Rhz,      ip->c_prec, ip->c_SW,
+                                          ip->c_LW,   ip->c_SW_dir, ip->c_LW_net, ip->c_TSurfObs, nullptr,    ip->c_Depth};
+    for (int t = 0; t < sim_len; ++t)
+      for (int v = 0; v < nvar; ++v)
+        hf[(static_cast<size_t>(t) * nvar + v) * ld + p] =
+            (v == RS_F_PHASE) ? static_cast<double>(ip->c_PrecPhase[t]) : src[v][t];
+    const LocalParameters& lp = *local[p];
+    const double row[RS_L_NLOCAL] = {lp.tair_relax, lp.VZ_relax, lp.RH_relax, lp.couplingTsurf, lp.lat, lp.lon,
+                                     lp.sky_view, static_cast<double>(lp.couplingIndexI),
+                                     static_cast<double>(lp.InitLenI), 1.0};
+    for (int k = 0; k < RS_L_NLOCAL; ++k) hl[k * ld + p] = row[k];
+    if (any_sky)
+      for (int k = 0; k < 360; ++k) hh[static_cast<size_t>(k) * ld + p] = ip->c_local_horizons[k];
+    s->outs[p] = *out[p];
+    double* o[RS_O_NVAR] = {out[p]->c_TsurfOut, out[p]->c_SnowOut,    out[p]->c_WaterOut,
+                            out[p]->c_IceOut,   out[p]->c_DepositOut, out[p]->c_Ice2Out};
+    for (int v = 0; v < RS_O_NVAR; ++v)
+      for (int t = 0; t < sim_len; ++t) o[v][t] = -9999.0;
+  }
+  CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CU(cudaMalloc(&s->d_forcing, sizeof(double) * hf.size()));
+  CU(cudaMalloc(&s->d_local, sizeof(double) * hl.size()));
+  if (any_sky) CU(cudaMalloc(&s->d_hor, sizeof(double) * hh.size()));
+  CU(cudaMalloc(&s->d_out, sizeof(double) * RS_O_NVAR * sim_len * ld));
+  CU(cudaMalloc(&s->d_state, sizeof(double) * RS_STATE_NPLANES(nl) * ld));
+  CU(cudaMalloc(&s->d_scratch, sizeof(double) * RS_SCRATCH_NPLANES(nl) * ld));
+  CU(cudaMalloc(&s->d_solar, sizeof(double) * 4 * sim_len));
+  CU(cudaMalloc(&s->d_tf, sizeof(int) * 6 * sim_len));
+  CU(cudaMalloc(&s->d_status, sizeof(int) * ld));
+  CU(cudaMalloc(&s->d_counters, sizeof(unsigned long long) * RS_CNT_N));
+  CU(cudaMemcpyAsync(s->d_forcing, hf.data(), sizeof(double) * hf.size(), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->d_local, hl.data(), sizeof(double) * hl.size(), cudaMemcpyHostToDevice, s->stream));
+  if (any_sky) CU(cudaMemcpyAsync(s->d_hor, hh.data(), sizeof(double) * hh.size(), cudaMemcpyHostToDevice, s->stream));
+  const int* tf[6] = {in[0]->c_year, in[0]->c_month, in[0]->c_day, in[0]->c_hour, in[0]->c_minute, in[0]->c_second};
+  for (int k = 0; k < 6; ++k)
+    CU(cudaMemcpyAsync(s->d_tf + static_cast<size_t>(k) * sim_len, tf[k], sizeof(int) * sim_len, cudaMemcpyHostToDevice,
+                       s->stream));
+  CU(cudaMemsetAsync(s->d_status, 0, sizeof(int) * ld, s->stream));
+  CU(cudaMemsetAsync(s->d_counters, 0, sizeof(unsigned long long) * RS_CNT_N, s->stream));
+  CU(static_cast<cudaError_t>(rs_launch_fill(s->d_out, static_cast<long long>(RS_O_NVAR) * sim_len * ld, -9999.0, s->stream)));
+  CU(static_cast<cudaError_t>(rs_launch_solar(s->d_tf, sim_len, s->d_solar, s->stream)));
+  g_launches_total += 2;
+  CU(cudaStreamSynchronize(s->stream));  // the host staging vectors die with this frame
+  *session = guard.release();
+  return RS_OK;
+}
+
+int roadsurf_session_set_chunk(void* session, int steps)
+{
+  RsSession* s = session_of(session);
+  if (!s) return fail(RS_ERR_BAD_ARGUMENT, "not a session");
+  s->chunk = steps > 1 ? steps : 1;
+  return RS_OK;
+}
+
+int roadsurf_session_done(void* session)
+{
+  RsSession* s = session_of(session);
+  return s ? s->done : RS_ERR_BAD_ARGUMENT;
+}
+
+int roadsurf_step(void* session, int i)
+{
+  RsSession* s = session_of(session);
+  if (!s) return fail(RS_ERR_BAD_ARGUMENT, "not a session");
+  if (i < 1 || i > s->sim_len) return fail(RS_ERR_BAD_ARGUMENT, "step outside [1, SimLen]");
+  if (i <= s->done) return RS_OK;
+  int current = 0;
+  CU(cudaGetDevice(&current));
+  if (current != s->device) CU(cudaSetDevice(s->device));
+  const int begin = s->done + 1;
+  int target = std::min(s->sim_len, std::max(i, s->done + s->chunk));
+  // a coupling window [start, end + 1] is indivisible: its rewinds happen inside the kernel
+  if (s->wend > 0 && begin <= s->wend + 1 && target >= s->wstart) target = std::max(target, std::min(s->wend + 1, s->sim_len));
+  {
+    std::lock_guard<std::mutex> device_lock(g_device_mu[s->device & 63]);
+    RsModel m;
+    // (another caller may have replaced the device's model since the session was opened)
+    {
+      std::lock_guard<std::mutex> lk(g_model_mu);
+      DeviceModel& dm = g_models[s->device];
+      if (!dm.valid || std::memcmp(&dm.m, &s->model, sizeof m) != 0)
+      {
+        for (auto& kv : dm.last_launch) CU(cudaEventSynchronize(kv.second));
+        CU(static_cast<cudaError_t>(rs_upload_model(&s->model)));
+        dm.m = s->model;
+        dm.valid = true;
+      }
+    }
+    RsArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.npoints = s->npoints;
+    a.ld = s->ld;
+    a.sim_len = s->sim_len;
+    a.n_records = s->sim_len;
+    a.nvar = s->nvar;
+    a.out_stride = 1;
+    a.n_out = s->sim_len;
+    a.forcing_mode = 0;
+    a.step_begin = begin;
+    a.step_end = target;
+    a.forcing_step0 = 1;
+    a.forcing = s->d_forcing;
+    a.tf = s->d_tf;
+    a.local = s->d_local;
+    a.horizons = s->d_hor;
+    a.solar = s->d_solar;
+    a.out = s->d_out;
+    a.status = s->d_status;
+    a.scratch = s->d_scratch;
+    RsArgsCold ac;
+    std::memset(&ac, 0, sizeof ac);
+    ac.state = s->d_state;
+    ac.counters = s->d_counters;
+    ac.out_nvar = RS_O_NVAR;
+    RsLaunchInfo li;
+    std::memset(&li, 0, sizeof li);
+    int n = 0;
+    const int rc = launch_model(a, ac, s->model, 0, s->stream, &li, &n);
+    if (rc != RS_OK) return rc;
+    g_launches_total += n;
+    li.nlayers = s->nl;
+    li.launches_total = g_launches_total;
+    g_launch = li;
+    CU(cudaStreamSynchronize(s->stream));
+  }
+  s->done = target;
+  if (current != s->device) cudaSetDevice(current);
+  return RS_OK;
+}
+
+int roadsurf_session_fetch(void* session, int i, int* status)
+{
+  RsSession* s = session_of(session);
+  if (!s) return fail(RS_ERR_BAD_ARGUMENT, "not a session");
+  if (i > s->done) return fail(RS_ERR_BAD_ARGUMENT, "step not executed yet: call roadsurf_step first");
+  int current = 0;
+  CU(cudaGetDevice(&current));
+  if (current != s->device) CU(cudaSetDevice(s->device));
+  // deliver every executed step not yet delivered; the steps of a coupling window were overwritten by the
+  // kernel's re-runs before they became visible here
+  const int t0 = s->fetched, n = s->done - s->fetched;
+  if (n > 0)
+  {
+    std::vector<double> h(static_cast<size_t>(RS_O_NVAR) * n * s->ld);
+    for (int v = 0; v < RS_O_NVAR; ++v)
+      CU(cudaMemcpy(h.data() + static_cast<size_t>(v) * n * s->ld,
+                    s->d_out + (static_cast<size_t>(v) * s->sim_len + t0) * s->ld, sizeof(double) * n * s->ld,
+                    cudaMemcpyDeviceToHost));
+    for (int p = 0; p < s->npoints; ++p)
+    {
+      OutputPointers& op = s->outs[p];
+      double* dst[RS_O_NVAR] = {op.c_TsurfOut, op.c_SnowOut, op.c_WaterOut, op.c_IceOut, op.c_DepositOut, op.c_Ice2Out};
+      for (int v = 0; v < RS_O_NVAR; ++v)
+        for (int t = 0; t < n; ++t) dst[v][t0 + t] = h[(static_cast<size_t>(v) * n + t) * s->ld + p];
+    }
+    s->fetched = s->done;
+  }
+  if (status) CU(cudaMemcpy(status, s->d_status, sizeof(int) * s->npoints, cudaMemcpyDeviceToHost));
+  if (current != s->device) cudaSetDevice(current);
+  return RS_OK;
+}
+
+void roadsurf_session_close(void* session)
+{
+  RsSession* s = session_of(session);
+  if (!s) return;
+  int current = 0;
+  cudaGetDevice(&current);
+  cudaSetDevice(s->device);
+  for (void* p : {static_cast<void*>(s->d_forcing), static_cast<void*>(s->d_local), static_cast<void*>(s->d_hor),
+                  static_cast<void*>(s->d_out), static_cast<void*>(s->d_state), static_cast<void*>(s->d_scratch),
+                  static_cast<void*>(s->d_solar), static_cast<void*>(s->d_tf), static_cast<void*>(s->d_status),
+                  static_cast<void*>(s->d_counters)})
+    if (p) cudaFree(p);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  cudaSetDevice(current);
+  s->magic = 0;
+  delete s;
 }
 
 const char* roadsurf_last_error(void) { return g_err.c_str(); }

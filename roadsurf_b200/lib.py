@@ -35,6 +35,8 @@ EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roa
            "roadsurf_measure_fp64_tflops", "roadsurf_selftest_arith", "roadsurf_selftest_libm", "roadsurf_runsimulation_counters", "roadsurf_order_points", "roadsurf_default_parameters",
            "roadsurf_default_settings", "roadsurf_set_option", "roadsurf_release_workspace",
            "roadsurf_last_launch", "roadsurf_prepare_statics", "roadsurf_release_statics",
+           "roadsurf_session_open", "roadsurf_step", "roadsurf_session_fetch", "roadsurf_session_set_chunk",
+           "roadsurf_session_done", "roadsurf_session_close",
            "roadsurf_version")
 
 
@@ -231,6 +233,51 @@ def run_host_soa(settings, params, forcing, time_fields, local, out, record_step
                      horizons=ptr(horizons), out=ptr(out), status=ptr(status),
                      coupling_window_end=int(coupling_window_end), statics=statics)
     _check(load().roadsurf_run_host_soa(C.byref(hb), C.byref(settings), C.byref(params), int(ngpus)))
+
+
+class Session:
+    """Step-granular run of a PointArrays on the device (roadsurf_session_open / roadsurf_step /
+    roadsurf_session_fetch): what the Fortran subroutine API of module RoadSurf forwards to."""
+
+    def __init__(self, arrays, settings, params, chunk=1):
+        lib = load()
+        P = C.POINTER
+        lib.roadsurf_session_open.argtypes = [C.c_int, P(P(abi.OutputPointers)), P(P(abi.InputPointers)),
+                                              P(abi.InputSettings), P(abi.InputParameters),
+                                              P(P(abi.LocalParameters)), P(C.c_void_p)]
+        lib.roadsurf_step.argtypes = [C.c_void_p, C.c_int]
+        lib.roadsurf_session_fetch.argtypes = [C.c_void_p, C.c_int, P(C.c_int)]
+        lib.roadsurf_session_set_chunk.argtypes = [C.c_void_p, C.c_int]
+        lib.roadsurf_session_done.argtypes = [C.c_void_p]
+        lib.roadsurf_session_close.argtypes = [C.c_void_p]
+        lib.roadsurf_session_close.restype = None
+        self._keep = (arrays.input_pointers(), arrays.output_pointers(), arrays)
+        ins, outs, _ = self._keep
+        self._ptrs = (abi.pointer_arrays(outs, abi.OutputPointers), abi.pointer_arrays(ins, abi.InputPointers),
+                      abi.pointer_arrays(arrays.local, abi.LocalParameters))
+        self.handle = C.c_void_p(None)
+        self.npoints = arrays.npoints
+        _check(lib.roadsurf_session_open(arrays.npoints, self._ptrs[0], self._ptrs[1], C.byref(settings),
+                                         C.byref(params), self._ptrs[2], C.byref(self.handle)))
+        if chunk > 1:
+            _check(lib.roadsurf_session_set_chunk(self.handle, int(chunk)))
+
+    def step(self, i):
+        _check(load().roadsurf_step(self.handle, int(i)))
+
+    def fetch(self, i):
+        status = np.zeros(self.npoints, dtype=np.int32)
+        _check(load().roadsurf_session_fetch(self.handle, int(i), status.ctypes.data_as(abi.c_int_p)))
+        return status
+
+    @property
+    def done(self):
+        return load().roadsurf_session_done(self.handle)
+
+    def close(self):
+        if self.handle:
+            load().roadsurf_session_close(self.handle)
+            self.handle = C.c_void_p(None)
 
 
 def runsimulation(arrays, settings, params, point=0):

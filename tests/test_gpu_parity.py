@@ -1003,3 +1003,67 @@ def test_prepared_statics_give_the_same_results_with_less_upload(rslib):
     small.run()
     torch.cuda.synchronize()
     assert torch.equal(want.cuda(), small.out[:, :, idx])
+
+
+def _stepwise(rslib, arrays, settings, params, chunk=1, stop_when_failed=True):
+    """Drive a session the way examples/example1/src/Simulation.f90 drives the library: one step per loop
+    trip, outputs fetched after every step, the loop ends when the (single) point has failed."""
+    sess = rslib.Session(arrays, settings, params, chunk=chunk)
+    launches0 = rslib.last_launch()["launches_total"]
+    try:
+        i = 1
+        status = np.zeros(arrays.npoints, dtype=np.int32)
+        while i < settings.SimLen:
+            sess.step(i)
+            status = sess.fetch(i)
+            if stop_when_failed and arrays.npoints == 1 and (status[0] & rslib.ST_FAILED):
+                break
+            i += 1
+        else:
+            sess.step(settings.SimLen)            # lastValues + the final step (Simulation.f90:100-115)
+            status = sess.fetch(settings.SimLen)
+        return status, rslib.last_launch()["launches_total"] - launches0
+    finally:
+        sess.close()
+
+
+def test_stepwise_session_equals_the_single_launch(rslib):
+    """roadsurf_step (one launch per model step on the resumable path, state resident on the device) against
+    roadsurf_run_batch: bit-identical outputs and status words -- plain forecast with sky-view points and a
+    point that fails in the middle; a coupled run, whose window is indivisible; run-ahead chunks."""
+    arrays, settings, params, _ = synth.make_case(40, 2, seed=350)
+    arrays.tair[3, 100] = 333.0                                       # CheckValues fails point 3 at step 101
+    ref = arrays.copy()
+    st_ref = rslib.run_batch(ref, settings, params)
+    for chunk in (1, 37):
+        work = arrays.copy()
+        st, launches = _stepwise(rslib, work, settings, params, chunk=chunk)
+        for k in ref.out:
+            assert np.array_equal(work.out[k], ref.out[k], equal_nan=True), (chunk, k)
+        assert np.array_equal(st, st_ref)
+        assert (launches >= settings.SimLen) if chunk == 1 else (launches < 12)
+    assert st_ref[3] & rslib.ST_FAILED and (ref.out["TsurfOut"][3, 101:] == -9999.0).all()
+
+    arrays, settings, params, _ = synth.make_case(33, 1, seed=351, analysis_hours=2, use_coupling=1, use_relaxation=1,
+                                                   settings_kw=dict(coupling_minutes=60))
+    ref = arrays.copy()
+    st_ref = rslib.run_batch(ref, settings, params)
+    work = arrays.copy()
+    st, launches = _stepwise(rslib, work, settings, params)
+    for k in ref.out:
+        assert np.array_equal(work.out[k], ref.out[k], equal_nan=True), k
+    assert np.array_equal(st, st_ref) and (st & rslib.ST_COUPLING_USED).all()
+    window = 60 * 60 // 30
+    assert settings.SimLen - window - 2 <= launches <= settings.SimLen - window + 2   # the window was one launch
+
+
+def test_stepwise_single_point_like_the_fortran_main(rslib, oracle):
+    """One point, one step per call, stop at failure: the call pattern of the Fortran main against the oracle."""
+    arrays, settings, params, _ = synth.make_case(1, 1, seed=352, sky_view_fraction=1.0)
+    arrays.SW[0, 60] = -50.0
+    ref = arrays.copy()
+    st_cpu, _ = oracle.run_batch(ref, settings, params)
+    st, _ = _stepwise(rslib, arrays, settings, params)
+    for k in ref.out:
+        assert np.array_equal(arrays.out[k], ref.out[k], equal_nan=True), k
+    assert st[0] == st_cpu[0] and (st[0] & rslib.ST_FAILED)
