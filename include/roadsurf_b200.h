@@ -283,7 +283,11 @@ typedef struct RsDeviceBatch
   int ld;
   int sim_len;          /* SimLen: number of model steps */
   int forcing_mode;     /* 0: one forcing record per model step.  1: coarse records, linear
-                           interpolation in time on the device (JsonSource.cpp:49-176). */
+                           interpolation in time inside the step kernel (example1's rule,
+                           JsonSource.cpp:49-176).  2: coarse records interpolated by example2's rule
+                           (AsciiSource.cpp:223-281: per variable the nearest valid records, at most
+                           180 minutes apart, whole-minute weights) by an expansion pass into
+                           `expand_workspace`, chunk by chunk, ahead of the step kernel. */
   int n_records;        /* forcing_mode 0: == sim_len.  1: number of coarse records */
   int nvar;             /* RS_F_NVAR or RS_F_NVAR_DEPTH */
   const double* forcing;      /* [n_records][nvar][ld] */
@@ -325,6 +329,9 @@ typedef struct RsDeviceBatch
                                  on a grid with 30 % of them scattered); roadsurf_order_points builds
                                  the permutation.  Results do not depend on it.  Recommended with
                                  coarse forcing (per-step loads of a permuted warp are gathers). */
+  double* expand_workspace;   /* forcing_mode 2: [expand_steps][nvar][ld] device work space */
+  int expand_steps;           /* forcing_mode 2: model steps per expansion chunk (>= 1).  More than one
+                                 chunk needs `state`; with coupling a chunk must hold a whole window */
   int coupling_window_end;    /* 0, or the caller's assertion that every coupled point of the batch has
                                  couplingIndexI == this value (points that do not are flagged
                                  RS_ST_BAD_WINDOW).  With `state` and `scratch` present it enables lane
@@ -467,6 +474,14 @@ int roadsurf_fill(double* dst, int64_t n, double value, void* stream);
 /* Measure the fp64 FMA throughput of the current device (TFLOP/s, FMA = 2 flop) with a
  * register-resident DFMA kernel; used as the fp64 roofline denominator by bench.py. */
 double roadsurf_measure_fp64_tflops(int iterations);
+
+/* The expansion pass of forcing_mode 2 on its own: coarse records -> one record per model step for the
+ * steps [step_begin, step_end] into dst [step_end - step_begin + 1][nvar][ld] (device memory).  `records`
+ * supplies forcing, record_step, n_records, nvar, ld, npoints; the time step is the current model's.
+ * rule 1: example1's interpolation (what forcing_mode 1 does inside the step kernel); rule 2: example2's.
+ * Asynchronous on `stream`. */
+int roadsurf_expand_records(const RsDeviceBatch* records, int rule, int step_begin, int step_end, double* dst,
+                            void* stream);
 
 /* Builds RsDeviceBatch.order on the device: the slots of points without sky-view radiation first, those
  * with it last, original order kept inside both classes.  `local` is the batch's [RS_L_NLOCAL][ld]

@@ -43,6 +43,9 @@ def _declare(lib):
     lib.oracle_run_batch_state.argtypes = [C.c_int, _P(_P(OP)), _P(_P(IP)), _P(IS), _P(IPa), _P(_P(LP)),
                                            C.c_int, _P(C.c_int), abi.c_double_p, abi.c_double_p]
     lib.oracle_run_batch_state.restype = None
+    lib.oracle_interpolate_example2.argtypes = [abi.c_double_p, abi.c_int_p, C.c_int, C.c_double, C.c_int, C.c_int,
+                                                C.c_double, abi.c_double_p]
+    lib.oracle_interpolate_example2.restype = None
     lib.oracle_count_ops.argtypes = [_P(OP), _P(IP), _P(IS), _P(IPa), _P(LP), _P(C.c_ulonglong)]
     lib.oracle_count_ops.restype = C.c_longlong
     lib.oracle_layer_depths.argtypes = [C.c_int, abi.c_double_p]
@@ -168,6 +171,18 @@ def run_batch_state(arrays, settings, params, nthreads=1):
                                int(nthreads), status.ctypes.data_as(abi.c_int_p), tmp.ctypes.data_as(abi.c_double_p),
                                surf.ctypes.data_as(abi.c_double_p))
     return status, tmp, surf
+
+
+def interpolate_example2(raw, record_step, dt_secs, sim_len, kind=0, fill=-9999.9):
+    """example2's time interpolation (AsciiSource.cpp:223-345) of one raw series [nrec] -> numpy [sim_len].
+    kind 0 plain, 1 relative humidity, 2 precipitation, 3 precipitation phase."""
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    rs = np.ascontiguousarray(record_step, dtype=np.int32)
+    out = np.empty(int(sim_len))
+    load(False).oracle_interpolate_example2(raw.ctypes.data_as(abi.c_double_p), rs.ctypes.data_as(abi.c_int_p), len(rs),
+                                            float(dt_secs), int(sim_len), int(kind), float(fill),
+                                            out.ctypes.data_as(abi.c_double_p))
+    return out
 
 
 def count_ops(arrays, settings, params, point=0):

@@ -7,6 +7,7 @@
 //                      reference) -- the timing baseline "compiled like the reference"
 #include "roadsurf_oracle.hpp"
 
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <thread>
@@ -199,6 +200,77 @@ long long oracle_count_ops(OutputPointers* out, const InputPointers* in, const I
   counts[7] = g_ops.pow;
   counts[8] = g_ops.cmp;
   return m.diag.executed_steps;
+}
+
+// ---- example2's time interpolation of raw records (examples/example2/src/AsciiSource.cpp) --------
+
+// AsciiSource::Impl::interpolate (:223-281) + the per-time loop of GetWeather (:292-345) for ONE variable
+// of one point: raw[nrec] at model steps record_step[nrec] (times = step * DT seconds; the reference's
+// NFmiMetTime::DifferenceInMinutes is taken as whole minutes) -> out[sim_len], left at `fill` where the
+// reference assigns nothing.  kind 0: plain; 1: relative humidity (clamped to [0, 100], :322-323);
+// 2: precipitation (> 100 dropped, :326-327); 3: precipitation phase (interpolated as a double, then
+// stored into the int array, :345: truncation).  A value is missing when NaN or < -9000 (read_file
+// :150-165 leaves MISSING = NaN where the file has -9999).
+void oracle_interpolate_example2(const double* raw, const int* record_step, int nrec, double DT, int sim_len, int kind,
+                                 double fill, double* out)
+{
+  auto is_missing = [](double x) { return std::isnan(x) || x < -9000.0; };
+  auto minutes = [&](int steps) { return static_cast<long long>(static_cast<double>(steps) * DT) / 60; };
+  const double MISSING = std::nan("");
+  for (int i = 0; i < sim_len; ++i)
+  {
+    out[i] = fill;
+    // :307-308 not in the time interval of the data
+    if (nrec < 1 || i < record_step[0] || i > record_step[nrec - 1]) continue;
+    // :313-316 first position where t >= time
+    int pos = 0;
+    while (pos < nrec && record_step[pos] < i) ++pos;
+    double value = MISSING;
+    bool done = false;
+    // :228-233
+    if (record_step[pos] == i && !is_missing(raw[pos]))
+    {
+      value = raw[pos];
+      done = true;
+    }
+    // :235-236
+    if (!done && pos == 0) done = true;
+    if (!done)
+    {
+      // :240-250 first valid value at or after
+      int pos2;
+      double value2 = MISSING;
+      for (pos2 = pos; pos2 < nrec; ++pos2)
+      {
+        value2 = raw[pos2];
+        if (!is_missing(value2)) break;
+      }
+      if (!is_missing(value2))
+      {
+        // :254-264 first valid value before
+        int pos1;
+        double value1 = MISSING;
+        for (pos1 = pos - 1;; --pos1)
+        {
+          value1 = raw[pos1];
+          if (pos1 == 0 || !is_missing(value1)) break;
+        }
+        if (!is_missing(value1))
+        {
+          // :268-279
+          const long long gap = minutes(record_step[pos2] - record_step[pos1]);
+          if (gap <= 180 && gap > 0)
+          {
+            const long long gap1 = minutes(i - record_step[pos1]);
+            value = (static_cast<double>(gap - gap1) * value1 + static_cast<double>(gap1) * value2) / static_cast<double>(gap);
+          }
+        }
+      }
+    }
+    if (kind == 1 && !is_missing(value)) value = std::max(0.0, std::min(100.0, value));
+    if (kind == 2 && value > 100) value = MISSING;
+    if (!is_missing(value)) out[i] = (kind == 3) ? static_cast<double>(static_cast<int>(value)) : value;
+  }
 }
 
 // ---- unit-level entry points for the known-answer tests ---------------------------------------

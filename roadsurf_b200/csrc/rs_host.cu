@@ -1517,12 +1517,19 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
     if (b->n_records < step_end - forcing_step0 + 1)
       return fail(RS_ERR_BAD_ARGUMENT, "forcing_mode 0 needs n_records >= step_end - forcing_step0 + 1");
   }
-  else if (b->forcing_mode == 1)
+  else if (b->forcing_mode == 1 || b->forcing_mode == 2)
   {
     if (b->n_records < 2 || !b->record_step) return fail(RS_ERR_BAD_ARGUMENT, "coarse forcing needs >= 2 records");
+    if (b->forcing_mode == 2)
+    {
+      if (!b->expand_workspace || b->expand_steps < 1)
+        return fail(RS_ERR_BAD_ARGUMENT, "forcing_mode 2 needs expand_workspace and expand_steps >= 1");
+      if (b->expand_steps < step_end - step_begin + 1 && !b->state)
+        return fail(RS_ERR_BAD_ARGUMENT, "forcing_mode 2 in several chunks needs batch->state");
+    }
   }
   else
-    return fail(RS_ERR_BAD_ARGUMENT, "forcing_mode must be 0 or 1");
+    return fail(RS_ERR_BAD_ARGUMENT, "forcing_mode must be 0, 1 or 2");
   if (m.use_coupling && !b->scratch) return fail(RS_ERR_BAD_ARGUMENT, "coupling needs batch->scratch");
   RsArgs a;
   std::memset(&a, 0, sizeof a);
@@ -1563,6 +1570,29 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   CU(static_cast<cudaError_t>(rs_launch_solar(b->time_fields, b->sim_len, b->solar, stream)));
   ++g_launches_total;
 
+  if (b->forcing_mode == 2)
+  {
+    // expansion pass + full-resolution step kernel, chunk by chunk through the resumable path
+    for (int cb = step_begin; cb <= step_end; cb += b->expand_steps)
+    {
+      const int ce = std::min(step_end, cb + b->expand_steps - 1);
+      CU(static_cast<cudaError_t>(rs_launch_expand(b->forcing, b->record_step, b->n_records, b->nvar, b->ld, b->npoints, 2,
+                                                    m.DT, cb, ce, b->expand_workspace, stream)));
+      RsArgs ak = a;
+      ak.forcing_mode = 0;
+      ak.forcing = b->expand_workspace;
+      ak.n_records = ce - cb + 1;
+      ak.forcing_step0 = cb;
+      ak.step_begin = cb;
+      ak.step_end = ce;
+      int n = 0;
+      const int rc = launch_model(ak, ac, m, 0, stream, &li, &n);
+      if (rc != RS_OK) return rc;
+      g_launches_total += n + 1;
+    }
+    --g_launches_total;  // (the last one is counted below)
+  }
+  else
   {
     int n = 0;
     const int rc = launch_model(a, ac, m, b->coupling_window_end, stream, &li, &n);
@@ -1577,6 +1607,27 @@ int roadsurf_run_device(const RsDeviceBatch* b, void* stream)
   li.forcing_mode = b->forcing_mode;
   li.launches_total = ++g_launches_total;
   g_launch = li;
+  return RS_OK;
+}
+
+int roadsurf_expand_records(const RsDeviceBatch* b, int rule, int step_begin, int step_end, double* dst, void* stream)
+{
+  if (!b || !dst || !b->forcing || !b->record_step || b->n_records < 2 || (rule != 1 && rule != 2) || step_begin < 1 ||
+      step_end < step_begin || b->ld < 32 || b->ld % 32 != 0)
+    return fail(RS_ERR_BAD_ARGUMENT, "bad arguments");
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  double DT;
+  {
+    std::lock_guard<std::mutex> lk(g_model_mu);
+    auto it = g_models.find(dev);
+    if (it == g_models.end() || !it->second.valid)
+      return fail(RS_ERR_BAD_ARGUMENT, "roadsurf_set_model was not called on this device");
+    DT = it->second.m.DT;
+  }
+  CU(static_cast<cudaError_t>(rs_launch_expand(b->forcing, b->record_step, b->n_records, b->nvar, b->ld, b->npoints, rule, DT,
+                                                step_begin, step_end, dst, stream)));
+  ++g_launches_total;
   return RS_OK;
 }
 

@@ -56,6 +56,9 @@ enum
 // Host-callable launchers (rs_kernel.cu).  Return a cudaError_t as int.
 int rs_upload_model(const RsModel* m);
 int rs_launch_solar(const int* tf, int sim_len, double* table, void* stream);
+// coarse records -> per-step forcing [step_end - step_begin + 1][nvar][ld]; rule 1 = example1, 2 = example2
+int rs_launch_expand(const double* rec, const int* record_step, int n_records, int nvar, int ld, int npoints, int rule,
+                     double DT, int step_begin, int step_end, double* dst, void* stream);
 int rs_launch_partition(const double* flags_plane, int ld, int npoints, int sorted, int* index, int* n_index, void* stream);
 // `coupling`: the model has use_coupling set; `depth`: it has a fixed output depth (depth_mode != 0).  Both select
 // the kernel variant compiled with exactly the features the run needs.

@@ -36,7 +36,7 @@ EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roa
            "roadsurf_default_settings", "roadsurf_set_option", "roadsurf_release_workspace",
            "roadsurf_last_launch", "roadsurf_prepare_statics", "roadsurf_release_statics",
            "roadsurf_session_open", "roadsurf_step", "roadsurf_session_fetch", "roadsurf_session_set_chunk",
-           "roadsurf_session_done", "roadsurf_session_close",
+           "roadsurf_session_done", "roadsurf_session_close", "roadsurf_expand_records",
            "roadsurf_version")
 
 
@@ -70,7 +70,8 @@ class RsDeviceBatch(C.Structure):
                 ("state", C.c_void_p), ("scratch", C.c_void_p), ("counters", C.c_void_p),
                 ("solar", C.c_void_p), ("step_begin", C.c_int), ("step_end", C.c_int),
                 ("forcing_step0", C.c_int), ("out_slot0", C.c_int), ("out_start", C.c_int),
-                ("out_nvar", C.c_int), ("order", C.c_void_p), ("coupling_window_end", C.c_int)]
+                ("out_nvar", C.c_int), ("order", C.c_void_p), ("expand_workspace", C.c_void_p),
+                ("expand_steps", C.c_int), ("coupling_window_end", C.c_int)]
 
 
 class RsHostBatch(C.Structure):
@@ -298,12 +299,14 @@ class DeviceBatch:
 
     def __init__(self, npoints, sim_len, nlayers=15, n_records=None, nvar=F_NVAR, out_stride=1,
                  coarse=False, horizons=False, coupling=False, state=False, device="cuda",
-                 out_start=0, extended_outputs=False):
+                 out_start=0, extended_outputs=False, rule=1, expand_steps=0):
         import torch
         self.torch = torch
         self.npoints, self.sim_len, self.nlayers = int(npoints), int(sim_len), int(nlayers)
         self.ld = (self.npoints + 31) // 32 * 32
         self.coarse = bool(coarse)
+        self.rule = int(rule)           # coarse records: 1 = example1's interpolation (in the step kernel), 2 = example2's
+        self.expand_steps = int(expand_steps) if expand_steps else self.sim_len
         self.n_records = int(n_records) if coarse else self.sim_len
         self.nvar = int(nvar)
         self.out_stride = int(out_stride)
@@ -329,6 +332,8 @@ class DeviceBatch:
         self.scratch = torch.zeros((scratch_nplanes(nlayers), self.ld), **f64) if coupling else None
         self.counters = torch.zeros(CNT_N, dtype=torch.int64, device=device)
         self.solar = torch.zeros((self.sim_len, 4), **f64)
+        self.expand_workspace = (torch.zeros((self.expand_steps, self.nvar, self.ld), **f64)
+                                 if (coarse and self.rule == 2) else None)
 
     def descriptor(self, step_begin=0, step_end=0, forcing=None, forcing_step0=0, out=None, out_slot0=0):
         def ptr(t):
@@ -338,7 +343,8 @@ class DeviceBatch:
         n_records = forcing.shape[0]
         return RsDeviceBatch(step_begin=step_begin, step_end=step_end, forcing_step0=forcing_step0,
                              out_slot0=out_slot0, npoints=self.npoints, ld=self.ld, sim_len=self.sim_len,
-                             forcing_mode=1 if self.coarse else 0, n_records=n_records,
+                             forcing_mode=(2 if self.rule == 2 else 1) if self.coarse else 0, n_records=n_records,
+                             expand_workspace=ptr(self.expand_workspace), expand_steps=self.expand_steps,
                              nvar=self.nvar, forcing=ptr(forcing), record_step=ptr(self.record_step),
                              time_fields=ptr(self.time_fields), local=ptr(self.local),
                              horizons=ptr(self.horizons), out=ptr(out), out_stride=self.out_stride,
@@ -363,6 +369,19 @@ class DeviceBatch:
         st = stream if stream is not None else self.torch.cuda.current_stream()
         desc = self.descriptor(**chunk)
         _check(load().roadsurf_run_device(C.byref(desc), C.c_void_p(st.cuda_stream)))
+
+    def expand(self, rule, step_begin, step_end, stream=None):
+        """roadsurf_expand_records: the records interpolated to the steps [step_begin, step_end] as a new
+        device tensor [steps, nvar, ld] (rule 1 = example1, 2 = example2)."""
+        st = stream if stream is not None else self.torch.cuda.current_stream()
+        dst = self.torch.empty((step_end - step_begin + 1, self.nvar, self.ld), dtype=self.torch.float64,
+                               device=self.forcing.device)
+        lib = load()
+        lib.roadsurf_expand_records.argtypes = [C.POINTER(RsDeviceBatch), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        desc = self.descriptor()
+        _check(lib.roadsurf_expand_records(C.byref(desc), int(rule), int(step_begin), int(step_end),
+                                           C.c_void_p(dst.data_ptr()), C.c_void_p(st.cuda_stream)))
+        return dst
 
     # ---- helpers to fill the batch from host-layout data (tests, small cases) -----------------
     def load_point_arrays(self, arrays):

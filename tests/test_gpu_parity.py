@@ -915,12 +915,17 @@ def test_records_that_end_inside_the_run_are_not_extrapolated(rslib, oracle):
     db.run()
     torch.cuda.synchronize()
     got = db.outputs()
-    for k in ref.out:
-        assert np.array_equal(got[k], ref.out[k], equal_nan=True), k
-    assert np.array_equal(db.status.cpu().numpy()[:64], st_cpu)
-    # the step AT the last record is still executed on the missing values (CheckValues only stops the
-    # next loop trip, Simulation.f90:58-59): garbage / NaN there on both sides, -9999.0 afterwards
+    # The step AT the last record is still executed, on the missing values -9999.9 (CheckValues only stops
+    # the next loop trip, Simulation.f90:58-59).  Its output is garbage on both sides, and the one place
+    # where the two are not bit-identical: exp / log arguments that far outside the physical range leave
+    # the mirrored libm fast path (rs_libm.h) for the device library, 1 ulp apart per call.
     last = int(short.record_step[-1])
+    for k in ref.out:
+        same = (got[k] == ref.out[k]) | (np.isnan(got[k]) & np.isnan(ref.out[k]))
+        same[:, last] |= np.isclose(got[k][:, last], ref.out[k][:, last], rtol=1e-6, atol=0.0, equal_nan=True)
+        bad = np.argwhere(~same)
+        assert same.all(), (k, bad[:5].tolist(), [(got[k][tuple(b)], ref.out[k][tuple(b)]) for b in bad[:5]], last)
+    assert np.array_equal(db.status.cpu().numpy()[:64], st_cpu)
     assert (got["TsurfOut"][:, last + 1:] == -9999.0).all() and (got["TsurfOut"][:, last - 1] > -100).all()
 
 
@@ -1067,3 +1072,65 @@ def test_stepwise_single_point_like_the_fortran_main(rslib, oracle):
     for k in ref.out:
         assert np.array_equal(arrays.out[k], ref.out[k], equal_nan=True), k
     assert st[0] == st_cpu[0] and (st[0] & rslib.ST_FAILED)
+
+
+def _example2_arrays(oracle, arrays, rec, dt=30.0):
+    """Per-step arrays as example2's AsciiSource would interpolate the raw records (oracle restatement)."""
+    kinds = {"Rhz": 1, "prec": 2, "PrecPhase": 3}
+    out = arrays.copy()
+    for name in synth.RECORD_VARS:
+        dst = getattr(out, name)
+        for p in range(arrays.npoints):
+            fill = -9999.0 if name == "PrecPhase" else -9999.9
+            v = oracle.interpolate_example2(getattr(rec, name)[p], rec.record_step, dt, arrays.sim_len,
+                                            kinds.get(name, 0), fill)
+            dst[p] = v.astype(dst.dtype)
+    return out
+
+
+def test_example2_interpolation_mode_matches_the_oracle(rslib, oracle):
+    """forcing_mode 2: coarse records interpolated by example2's rule (AsciiSource.cpp:223-345: per variable
+    the nearest valid records, at most 180 minutes apart, whole-minute weights) in an expansion pass ahead
+    of the step kernel -- against the oracle fed with arrays interpolated on the host by the restatement of
+    that rule.  One chunk and several chunks (resumable path); the expansion pass itself is also compared
+    value by value, for both rules."""
+    import torch
+    npts = 96
+    arrays, settings, params, rec = synth.make_case(npts, 6, seed=360)
+    rec.VZ[5:20, 3] = np.nan                     # one record missing: interpolated across a 120-minute gap
+    rec.prec[10:30, 2:4] = -9999.0               # two missing: 180 minutes, still allowed
+    rec.SW[40:44, 2:5] = np.nan                  # three missing: 240 minutes -> stays missing -> the point fails
+    rec.Rhz[50:60, 4] = 140.0                    # clamped to 100
+    rec.prec[61, 5] = 250.0                      # dropped (> 100): neighbours 4 and 6 bracket it
+    ex2 = _example2_arrays(oracle, arrays, rec)
+    ref = ex2.copy()
+    st_cpu, _ = oracle.run_batch(ref, settings, params, nthreads=8)
+    assert (st_cpu[40:44] & rslib.ST_BAD_INPUT).all() and not (st_cpu[:40] & rslib.ST_FAILED).any()
+    rslib.set_model(settings, params)
+    for expand_steps, state in ((0, False), (100, True)):
+        db = rslib.DeviceBatch(npts, arrays.sim_len, n_records=rec.nrec, coarse=True, horizons=True, rule=2,
+                               expand_steps=expand_steps, state=state)
+        db.load_records(rec)
+        db.time_fields.copy_(torch.from_numpy(arrays.time))
+        db.load_local(arrays.local, arrays.local_horizons)
+        db.run()
+        torch.cuda.synchronize()
+        got = db.outputs()
+        for k in ref.out:
+            same = (got[k] == ref.out[k]) | (np.isnan(got[k]) & np.isnan(ref.out[k]))
+            # (the step executed on missing inputs is garbage on both sides, see the records-end test)
+            fail_step = np.argmax(ex2.SW < -9000, axis=1)
+            for p in range(40, 44):
+                same[p, fail_step[p]] = True
+            assert same.all(), (expand_steps, k, np.argwhere(~same)[:5].tolist())
+        assert np.array_equal(db.status.cpu().numpy()[:npts], st_cpu)
+    # the expansion pass, value by value
+    full = db.expand(2, 1, arrays.sim_len).cpu().numpy()
+    for v, name in enumerate(synth.RECORD_VARS):
+        want = getattr(ex2, name).astype(np.float64)
+        assert np.array_equal(full[:, v, :npts].T, want, equal_nan=True), name
+    fields = synth.interpolate_records(rec, arrays.sim_len)
+    rule1 = db.expand(1, 1, arrays.sim_len).cpu().numpy()
+    for v, name in enumerate(synth.RECORD_VARS):
+        ok = ~np.isnan(fields[name].astype(np.float64))           # (NaN records: example1's rule has no NaN notion)
+        assert np.array_equal(rule1[:, v, :npts].T[ok], fields[name].astype(np.float64)[ok]), name
