@@ -1,0 +1,49 @@
+"""N-version check: the C++ oracle against a second restatement written independently from the Fortran
+(oracle/py_restatement.py, plain Python, one point at a time) on the golden cases -- plain forecast with
+sky-view points, and analysis + forecast with coupling and relaxation.  Both are IEEE double without FMA on
+the same libm, so they must agree to rounding noise (1e-9 is the bar; in practice they agree exactly)."""
+import numpy as np
+import pytest
+
+from golden_io import CASE_NAMES, load_case
+from oracle import py_restatement
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_two_restatements_agree(oracle, name):
+    arrays, settings, params, golden, status, stride, steps = load_case(name)
+    ref = arrays.copy()
+    st, executed = oracle.run_batch(ref, settings, params, nthreads=2)
+    total, worst = 0, 0.0
+    for p in range(arrays.npoints):
+        out, nsteps, failed = py_restatement.run_point(arrays, settings, params, p)
+        total += nsteps
+        assert failed == bool(st[p] & 1)
+        for k, v in out.items():
+            d = np.abs(v - ref.out[k][p])
+            assert np.array_equal(np.isnan(v), np.isnan(ref.out[k][p])), (p, k)
+            worst = max(worst, float(np.nanmax(d)))
+            assert np.nanmax(d) < 1e-9, (name, p, k, int(np.nanargmax(d)), float(np.nanmax(d)))
+    assert total == executed          # same number of executed steps: the coupling re-runs agree too
+    print(f"{name}: max |difference| between the two restatements = {worst:.3e}")
+
+
+def test_second_restatement_layer_depths_and_sun():
+    """The pieces with REAL(4) arithmetic inside: layer depths (src/Initialization.f90:217-235) and the
+    Julian-day fraction (src/SunPosition.f90:245-253)."""
+    arrays, settings, params, *_ = load_case("plain")
+    pt = py_restatement.Point({k: getattr(arrays, v)[0] for k, v in
+                               dict(Tair="tair", Tdew="tdew", VZ="VZ", Rhz="Rhz", prec="prec", SW="SW", LW="LW", SW_dir="SW_dir",
+                                    LW_net="LW_net", TSurfObs="TSurfObs", PrecPhase="PrecPhase", Depth="Depth").items()}
+                              | {n: arrays.time[k] for k, n in enumerate(("year", "month", "day", "hour", "minute", "second"))}
+                              | {"local_horizons": arrays.local_horizons[0]}, settings, params, arrays.local[0])
+    pt.initialization()
+    # layer depths for N = 15 (m), four decimals
+    want = [0, 0.0303, 0.0647, 0.1049, 0.1532, 0.2127, 0.2881, 0.3857, 0.5143, 0.6863, 0.9191, 1.2370, 1.6741, 2.2781,
+            3.1156, 4.2801]
+    assert np.allclose(pt.Z[1:17], want, atol=5e-5)
+    from oracle import pyoracle
+    z = np.zeros(16)
+    from roadsurf_b200 import abi
+    pyoracle.load().oracle_layer_depths(15, z.ctypes.data_as(abi.c_double_p))
+    assert np.array_equal(np.array(pt.Z[1:17]), z)
