@@ -483,6 +483,13 @@ double roadsurf_measure_fp64_tflops(int iterations);
 int roadsurf_expand_records(const RsDeviceBatch* records, int rule, int step_begin, int step_end, double* dst,
                             void* stream);
 
+/* Diagnostic: the solar position (src/SunPosition.f90:20-194) exactly as the step kernel evaluates it, for
+ * every (step, point) pair.  Device pointers: time_fields [6][n_steps] (n_steps <= 65535), lat / lon [npoints]
+ * in degrees; elevation / azimuth [n_steps][npoints] in degrees, -9999.9 when the sun is down, NaN where the
+ * reference would `stop`.  Asynchronous on `stream`. */
+int roadsurf_sun_position(const int* time_fields, int n_steps, const double* lat, const double* lon, int npoints,
+                          double* elevation, double* azimuth, void* stream);
+
 /* Builds RsDeviceBatch.order on the device: the slots of points without sky-view radiation first, those
  * with it last, original order kept inside both classes.  `local` is the batch's [RS_L_NLOCAL][ld]
  * statics tensor, `order` receives ld ints.  Asynchronous on `stream`; call once per batch layout. */

@@ -46,6 +46,9 @@ def _declare(lib):
     lib.oracle_interpolate_example2.argtypes = [abi.c_double_p, abi.c_int_p, C.c_int, C.c_double, C.c_int, C.c_int,
                                                 C.c_double, abi.c_double_p]
     lib.oracle_interpolate_example2.restype = None
+    lib.oracle_sun_position_batch.argtypes = [abi.c_int_p, C.c_int, abi.c_double_p, abi.c_double_p, C.c_int, C.c_int,
+                                              abi.c_double_p, abi.c_double_p]
+    lib.oracle_sun_position_batch.restype = None
     lib.oracle_count_ops.argtypes = [_P(OP), _P(IP), _P(IS), _P(IPa), _P(LP), _P(C.c_ulonglong)]
     lib.oracle_count_ops.restype = C.c_longlong
     lib.oracle_layer_depths.argtypes = [C.c_int, abi.c_double_p]
@@ -183,6 +186,18 @@ def interpolate_example2(raw, record_step, dt_secs, sim_len, kind=0, fill=-9999.
                                             float(dt_secs), int(sim_len), int(kind), float(fill),
                                             out.ctypes.data_as(abi.c_double_p))
     return out
+
+
+def sun_position_batch(time_fields, lat, lon, nthreads=8):
+    """Solar position (src/SunPosition.f90) for every (step, point): time_fields [6, n] int32 -> (elev, azim) [n, npoints]."""
+    tf = np.ascontiguousarray(time_fields, dtype=np.int32)
+    lat, lon = np.ascontiguousarray(lat, dtype=np.float64), np.ascontiguousarray(lon, dtype=np.float64)
+    n, npts = tf.shape[1], lat.shape[0]
+    elev, azim = np.empty((n, npts)), np.empty((n, npts))
+    load(False).oracle_sun_position_batch(tf.ctypes.data_as(abi.c_int_p), n, lat.ctypes.data_as(abi.c_double_p),
+                                          lon.ctypes.data_as(abi.c_double_p), npts, int(nthreads),
+                                          elev.ctypes.data_as(abi.c_double_p), azim.ctypes.data_as(abi.c_double_p))
+    return elev, azim
 
 
 def count_ops(arrays, settings, params, point=0):

@@ -350,6 +350,34 @@ int oracle_sun_position(int year, int month, int day, int hour, int minute, int 
   return m.diag.solar_stop ? 1 : 0;
 }
 
+// oracle_sun_position for every (step, point) pair on `nthreads` threads: tf = [6][n_steps] time fields,
+// elevation / azimuth [n_steps][npoints]; NaN where the reference would `stop`.
+void oracle_sun_position_batch(const int* tf, int n_steps, const double* lat, const double* lon, int npoints, int nthreads,
+                               double* elevation, double* azimuth)
+{
+  if (nthreads < 1) nthreads = 1;
+  std::atomic<int> next(0);
+  auto worker = [&]() {
+    for (;;)
+    {
+      const int t = next.fetch_add(1);
+      if (t >= n_steps) break;
+      for (int p = 0; p < npoints; ++p)
+      {
+        double e, a;
+        const int stop = oracle_sun_position(tf[t], tf[n_steps + t], tf[2 * n_steps + t], tf[3 * n_steps + t],
+                                             tf[4 * n_steps + t], tf[5 * n_steps + t], lat[p], lon[p], &e, &a);
+        elevation[static_cast<size_t>(t) * npoints + p] = stop ? std::nan("") : e;
+        azimuth[static_cast<size_t>(t) * npoints + p] = stop ? std::nan("") : a;
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int k = 1; k < nthreads; ++k) pool.emplace_back(worker);
+  worker();
+  for (auto& th : pool) th.join();
+}
+
 // src/InputOutput.f90:239-268 and :202-236
 double oracle_calc_tdew(double t2m, double rh) { return Model<double>::CalcTDew(t2m, rh); }
 double oracle_calc_rh(double t2m, double tdew) { return Model<double>::CalcRhOne(t2m, tdew); }

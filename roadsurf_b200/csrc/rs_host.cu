@@ -1631,6 +1631,16 @@ int roadsurf_expand_records(const RsDeviceBatch* b, int rule, int step_begin, in
   return RS_OK;
 }
 
+int roadsurf_sun_position(const int* time_fields, int n_steps, const double* lat, const double* lon, int npoints,
+                          double* elevation, double* azimuth, void* stream)
+{
+  if (!time_fields || !lat || !lon || !elevation || !azimuth || n_steps < 1 || npoints < 1 || n_steps > 65535)
+    return fail(RS_ERR_BAD_ARGUMENT, "bad arguments (n_steps <= 65535 per call)");
+  CU(static_cast<cudaError_t>(rs_launch_sun_position(time_fields, n_steps, lat, lon, npoints, elevation, azimuth, stream)));
+  ++g_launches_total;
+  return RS_OK;
+}
+
 int roadsurf_order_points(const double* local, int ld, int npoints, int* order, void* stream)
 {
   if (!local || !order || ld < 32 || ld % 32 != 0 || npoints < 0 || npoints > ld)

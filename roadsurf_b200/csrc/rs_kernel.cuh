@@ -56,6 +56,8 @@ enum
 // Host-callable launchers (rs_kernel.cu).  Return a cudaError_t as int.
 int rs_upload_model(const RsModel* m);
 int rs_launch_solar(const int* tf, int sim_len, double* table, void* stream);
+int rs_launch_sun_position(const int* tf, int n_steps, const double* lat, const double* lon, int npoints, double* elev,
+                           double* azim, void* stream);
 // coarse records -> per-step forcing [step_end - step_begin + 1][nvar][ld]; rule 1 = example1, 2 = example2
 int rs_launch_expand(const double* rec, const int* record_step, int n_records, int nvar, int ld, int npoints, int rule,
                      double DT, int step_begin, int step_end, double* dst, void* stream);

@@ -37,6 +37,7 @@ EXPORTS = ("runsimulation", "roadsurf_last_error", "roadsurf_device_count", "roa
            "roadsurf_last_launch", "roadsurf_prepare_statics", "roadsurf_release_statics",
            "roadsurf_session_open", "roadsurf_step", "roadsurf_session_fetch", "roadsurf_session_set_chunk",
            "roadsurf_session_done", "roadsurf_session_close", "roadsurf_expand_records",
+           "roadsurf_sun_position",
            "roadsurf_version")
 
 
@@ -470,6 +471,21 @@ def selftest_libm(n=2_000_000, seed=7):
     bad = (C.c_longlong * 2)()
     load().roadsurf_selftest_libm(int(n), int(seed), bad)
     return [int(b) for b in bad]
+
+
+def sun_position(time_fields, lat, lon):
+    """roadsurf_sun_position on torch CUDA tensors: time_fields [6, n] int32, lat / lon [npoints] f64 ->
+    (elevation, azimuth) [n, npoints]."""
+    import torch
+    n, npts = time_fields.shape[1], lat.shape[0]
+    elev = torch.empty((n, npts), dtype=torch.float64, device=lat.device)
+    azim = torch.empty_like(elev)
+    lib = load()
+    lib.roadsurf_sun_position.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+    _check(lib.roadsurf_sun_position(time_fields.data_ptr(), n, lat.data_ptr(), lon.data_ptr(), npts, elev.data_ptr(),
+                                     azim.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return elev, azim
 
 
 def set_option(name, value):

@@ -1134,3 +1134,78 @@ def test_example2_interpolation_mode_matches_the_oracle(rslib, oracle):
     for v, name in enumerate(synth.RECORD_VARS):
         ok = ~np.isnan(fields[name].astype(np.float64))           # (NaN records: example1's rule has no NaN notion)
         assert np.array_equal(rule1[:, v, :npts].T[ok], fields[name].astype(np.float64)[ok]), name
+
+
+def test_solar_geometry_decisions_equal_the_hosts_over_a_year(rslib, oracle):
+    """The solar geometry is the one place where the kernel still calls the device library's sin / cos / acos /
+    atan2 (exp and log mirror the host libm).  What the model takes from it are two decisions: the horizon index
+    NINT(azimuth) and `horizon > elevation` (src/ModRadiation.f90:41-49).  A year of half-hourly times x 600
+    locations over the reference's lat/lon box (1.05e7 evaluations): sun-up / sun-down pattern and NINT(azimuth)
+    must equal the oracle's everywhere, elevation and azimuth to 1e-9 degrees (a shadow decision could only flip
+    for a horizon angle within that distance of the elevation)."""
+    import datetime as dt
+    import torch
+    n, npts = 17520, 600
+    tf = synth.time_axis(dt.datetime(2019, 1, 1), n, 1800.0)
+    rng = np.random.Generator(np.random.PCG64(5))
+    lat, lon = rng.uniform(59.8, 69.9, npts), rng.uniform(20.0, 31.0, npts)
+    e_cpu, a_cpu = oracle.sun_position_batch(tf, lat, lon, nthreads=8)
+    e_gpu, a_gpu = rslib.sun_position(torch.from_numpy(tf).cuda(), torch.from_numpy(lat).cuda(), torch.from_numpy(lon).cuda())
+    e_gpu, a_gpu = e_gpu.cpu().numpy(), a_gpu.cpu().numpy()
+    assert not np.isnan(e_cpu).any() and not np.isnan(e_gpu).any()          # nobody would `stop`
+    up_cpu, up_gpu = e_cpu > 0, e_gpu > 0
+    assert np.array_equal(up_cpu, up_gpu)
+    assert 0.25 < up_cpu.mean() < 0.6
+    assert np.array_equal(np.rint(a_cpu[up_cpu]), np.rint(a_gpu[up_cpu])), "a horizon index differs"
+    de, da = np.abs(e_cpu - e_gpu)[up_cpu].max(), np.abs(a_cpu - a_gpu)[up_cpu].max()
+    print(f"solar geometry, {up_cpu.sum()} sun-up evaluations: max |d elevation| = {de:.2e} deg, max |d azimuth| = {da:.2e} deg, "
+          f"bit-identical elevations: {(e_cpu == e_gpu)[up_cpu].mean():.4f}")
+    assert de < 1e-9 and da < 1e-9
+
+
+def test_guard_planes_around_every_written_tensor_stay_intact(rslib):
+    """Stand-in for compute-sanitizer (closed on this pool): out, state, scratch, status, solar table and the
+    expansion work space are carved out of larger buffers filled with a sentinel; coupled run with lane compaction
+    (index lists), ragged point count, point order, chunked launches, forcing_mode 2 -- no write may land outside."""
+    import torch
+    SENT, G = -7.25e300, 4096
+
+    def guarded(t):
+        buf = torch.full((t.numel() + 2 * G,), SENT if t.dtype == torch.float64 else -77, dtype=t.dtype, device=t.device)
+        view = buf[G:G + t.numel()].view(t.shape)
+        view.copy_(t)
+        return buf, view
+
+    def intact(bufs):
+        for name, buf in bufs.items():
+            s = SENT if buf.dtype == torch.float64 else -77
+            assert bool((buf[:G] == s).all()) and bool((buf[-G:] == s).all()), f"write outside {name}"
+
+    npts = 1000 + 7
+    arrays, settings, params, rec = synth.make_case(npts, 4, seed=370, analysis_hours=3, use_coupling=1, use_relaxation=1,
+                                                    obs_bias=False, settings_kw=dict(coupling_minutes=60))
+    rslib.set_model(settings, params)
+    for mode in ("compaction+order", "chunks", "example2"):
+        db = rslib.DeviceBatch(npts, arrays.sim_len, n_records=rec.nrec, coarse=True, horizons=True, coupling=True, state=True,
+                               out_stride=7, rule=2 if mode == "example2" else 1, expand_steps=arrays.sim_len)
+        db.load_records(rec)
+        db.time_fields.copy_(torch.from_numpy(arrays.time))
+        db.load_local(arrays.local, arrays.local_horizons)
+        bufs = {}
+        for name in ("out", "state", "scratch", "status", "solar") + (("expand_workspace",) if mode == "example2" else ()):
+            bufs[name], view = guarded(getattr(db, name))
+            setattr(db, name, view)
+        if mode == "compaction+order":
+            db.build_order()
+            db.run()
+        elif mode == "chunks":
+            db.coupling_window_end = 0
+            wend = arrays.local[0].couplingIndexI
+            db.run(step_begin=1, step_end=wend + 1)
+            db.run(step_begin=wend + 2, step_end=arrays.sim_len)
+        else:
+            db.coupling_window_end = 0
+            db.run()
+        torch.cuda.synchronize()
+        intact(bufs)
+        assert (db.status[:npts] & rslib.ST_NOT_RUN).sum() == 0
