@@ -740,30 +740,46 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
       return RS_OK;
     };
 
-    size_t b = 0;
-    for (size_t s0 = 0; s0 < slots.size(); s0 += max_slots, ++b)
-    {
-      Ctx& c = ctx[b & 1];
+    // The helper threads reference this frame's lambdas and locals: whatever happens in the loop, they are
+    // joined (and, after an error, the batch streams drained: pooled buffers may still be in use by queued
+    // kernels and copies) before anything here goes out of scope.
+    const int loop_rc = [&]() -> int {
+      size_t b = 0;
+      for (size_t s0 = 0; s0 < slots.size(); s0 += max_slots, ++b)
       {
-        const int rc = finish(c);  // the batch that used this buffer set two rounds ago
+        Ctx& c = ctx[b & 1];
+        {
+          const int rc = finish(c);  // the batch that used this buffer set two rounds ago
+          if (rc != RS_OK) return rc;
+        }
+        c.s0 = s0;
+        c.ld = static_cast<int>(std::min(max_slots, slots.size() - s0));
+        {
+          const int rc = stage_in(c);
+          if (rc != RS_OK) return rc;
+        }
+        c.rc = RS_OK;
+        c.drain = std::thread([&stage_out, &c]() {
+          c.rc = stage_out(c);
+          if (c.rc != RS_OK) c.err = g_err;
+        });
+      }
+      for (int k = 0; k < 2; ++k)
+      {
+        const int rc = finish(ctx[k]);
         if (rc != RS_OK) return rc;
       }
-      c.s0 = s0;
-      c.ld = static_cast<int>(std::min(max_slots, slots.size() - s0));
-      {
-        const int rc = stage_in(c);
-        if (rc != RS_OK) return rc;
-      }
-      c.rc = RS_OK;
-      c.drain = std::thread([&stage_out, &c]() {
-        c.rc = stage_out(c);
-        if (c.rc != RS_OK) c.err = g_err;
-      });
-    }
-    for (int k = 0; k < 2; ++k)
+      return RS_OK;
+    }();
+    if (loop_rc != RS_OK)
     {
-      const int rc = finish(ctx[k]);
-      if (rc != RS_OK) return rc;
+      const std::string err = g_err;
+      for (int k = 0; k < 2; ++k)
+      {
+        if (ctx[k].drain.joinable()) ctx[k].drain.join();
+        if (ctx[k].st) cudaStreamSynchronize(ctx[k].st);
+      }
+      return fail(loop_rc, err);
     }
   }
   return RS_OK;
@@ -2011,6 +2027,13 @@ extern "C" void runsimulation(OutputPointers* outPointers, const InputPointers* 
     mark_not_computed(outPointers, inSettings);
     return;
   }
+  // arguments that would fail a whole batch are rejected here, for this caller only
+  if (inPointers->inputLen < inSettings->SimLen || outPointers->outputLen < inSettings->SimLen)
+  {
+    std::fprintf(stderr, "roadsurf_b200 runsimulation failed: inputLen/outputLen shorter than SimLen\n");
+    mark_not_computed(outPointers, inSettings);
+    return;
+  }
   PendingCall me;
   me.out = outPointers;
   me.in = inPointers;
@@ -2019,52 +2042,52 @@ extern "C" void runsimulation(OutputPointers* outPointers, const InputPointers* 
   me.local = localParam;
   std::unique_lock<std::mutex> lk(g_call_mu);
   g_call_queue.push_back(&me);
-  if (g_call_leader)
-    g_call_cv.wait(lk, [&] { return me.done; });  // a leader is at work: it (or a successor) will run this call
-  else
+  while (!me.done)
   {
+    if (g_call_leader)
+    {
+      // a leader is at work: it will run this call, or hand the leadership over when its own is done
+      g_call_cv.wait(lk, [&] { return me.done || !g_call_leader; });
+      continue;
+    }
+    // become the leader for ONE batch: everything queued with the same settings and parameters as this call
     g_call_leader = true;
     // callers of a thread pool arrive together: give them a moment to queue up (0.3 ms against a run
     // of tens of milliseconds), so that the first batch is not a single point
     g_call_cv.wait_for(lk, std::chrono::microseconds(300), [] { return false; });
-    while (!g_call_queue.empty())
+    std::vector<PendingCall*> batch, rest;
+    for (PendingCall* c : g_call_queue)
     {
-      // everything queued with the same settings and parameters as the oldest call
-      std::vector<PendingCall*> batch, rest;
-      const PendingCall* first = g_call_queue.front();
-      for (PendingCall* c : g_call_queue)
-      {
-        const bool same = !std::memcmp(c->settings, first->settings, sizeof(InputSettings)) &&
-                          !std::memcmp(c->params, first->params, sizeof(InputParameters));
-        (same ? batch : rest).push_back(c);
-      }
-      g_call_queue.swap(rest);
-      lk.unlock();
-      const int n = static_cast<int>(batch.size());
-      g_calls_total += n;
-      ++g_call_batches_total;
-      std::vector<OutputPointers*> outs(n);
-      std::vector<const InputPointers*> ins(n);
-      std::vector<const LocalParameters*> locs(n);
-      for (int k = 0; k < n; ++k)
-      {
-        outs[k] = batch[k]->out;
-        ins[k] = batch[k]->in;
-        locs[k] = batch[k]->local;
-      }
-      const int rc = roadsurf_run_batch(n, outs.data(), ins.data(), first->settings, first->params, locs.data(), 1,
-                                        nullptr);
-      const std::string err = (rc != RS_OK) ? std::string(roadsurf_last_error()) : std::string();
-      lk.lock();
-      for (PendingCall* c : batch)
-      {
-        c->rc = rc;
-        c->err = err;
-        c->done = true;
-      }
-      g_call_cv.notify_all();
+      const bool same = !std::memcmp(c->settings, me.settings, sizeof(InputSettings)) &&
+                        !std::memcmp(c->params, me.params, sizeof(InputParameters));
+      (same ? batch : rest).push_back(c);
     }
+    g_call_queue.swap(rest);
+    lk.unlock();
+    const int n = static_cast<int>(batch.size());
+    g_calls_total += n;
+    ++g_call_batches_total;
+    std::vector<OutputPointers*> outs(n);
+    std::vector<const InputPointers*> ins(n);
+    std::vector<const LocalParameters*> locs(n);
+    for (int k = 0; k < n; ++k)
+    {
+      outs[k] = batch[k]->out;
+      ins[k] = batch[k]->in;
+      locs[k] = batch[k]->local;
+    }
+    const int rc = roadsurf_run_batch(n, outs.data(), ins.data(), me.settings, me.params, locs.data(), 1, nullptr);
+    const std::string err = (rc != RS_OK) ? std::string(roadsurf_last_error()) : std::string();
+    lk.lock();
+    for (PendingCall* c : batch)
+    {
+      c->rc = rc;
+      c->err = err;
+      c->done = true;
+    }
+    // this caller's own call is in `batch`, hence done: the leadership goes to whoever still waits
     g_call_leader = false;
+    g_call_cv.notify_all();
   }
   lk.unlock();
   if (me.rc != RS_OK)
