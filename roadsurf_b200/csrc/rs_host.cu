@@ -2052,9 +2052,18 @@ extern "C" void runsimulation(OutputPointers* outPointers, const InputPointers* 
     }
     // become the leader for ONE batch: everything queued with the same settings and parameters as this call
     g_call_leader = true;
-    // callers of a thread pool arrive together: give them a moment to queue up (0.3 ms against a run
-    // of tens of milliseconds), so that the first batch is not a single point
-    g_call_cv.wait_for(lk, std::chrono::microseconds(300), [] { return false; });
+    // callers of a thread pool arrive together (and come back together after a batch): give them a moment
+    // to queue up -- at least 1 ms, up to 5 ms while the queue keeps growing, against a run of ~100 ms whatever
+    // the batch size -- so that a batch holds the whole pool and not its first arrival
+    {
+      size_t seen = g_call_queue.size();
+      for (int k = 0; k < 10; ++k)
+      {
+        g_call_cv.wait_for(lk, std::chrono::microseconds(500), [] { return false; });
+        if (k >= 1 && g_call_queue.size() == seen) break;
+        seen = g_call_queue.size();
+      }
+    }
     std::vector<PendingCall*> batch, rest;
     for (PendingCall* c : g_call_queue)
     {
