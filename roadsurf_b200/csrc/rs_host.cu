@@ -95,7 +95,7 @@ int launch_model(const RsArgs& a, const RsArgsCold& ac, const RsModel& m, int we
   if (!(m.use_coupling && wend > 0 && passes > 0 && ac.state && a.scratch && !(opt_staging() && a.forcing_mode == 0) &&
         a.forcing_step0 == 1 && a.step_begin <= 1 && wend + 1 < a.step_end))
   {
-    CU(static_cast<cudaError_t>(rs_launch_run(&a, &ac, m.nlayers, opt_staging(), m.use_coupling, m.depth_mode != 0, stream, &li->grid, &li->block,
+    CU(static_cast<cudaError_t>(rs_launch_run(&a, &ac, m.nlayers, opt_staging(), m.use_coupling, m.use_relaxation, m.depth_mode != 0, stream, &li->grid, &li->block,
                                               &li->regs_per_thread, &li->smem_bytes)));
     *launches = 1;
     return RS_OK;
@@ -108,7 +108,7 @@ int launch_model(const RsArgs& a, const RsArgsCold& ac, const RsModel& m, int we
   a1.step_end = wend;
   c1.mode = RS_MODE_SPLIT;
   c1.window_end = wend;
-  CU(static_cast<cudaError_t>(rs_launch_run(&a1, &c1, m.nlayers, 0, m.use_coupling, m.depth_mode != 0, stream, &li->grid, &li->block,
+  CU(static_cast<cudaError_t>(rs_launch_run(&a1, &c1, m.nlayers, 0, m.use_coupling, m.use_relaxation, m.depth_mode != 0, stream, &li->grid, &li->block,
                                             &li->regs_per_thread, &li->smem_bytes)));
   RsArgs a2 = a;
   RsArgsCold c2 = c1;
@@ -120,7 +120,7 @@ int launch_model(const RsArgs& a, const RsArgsCold& ac, const RsModel& m, int we
   for (int k = 0; k < passes; ++k)
   {
     CU(static_cast<cudaError_t>(rs_launch_partition(flags, a.ld, a.npoints, 0, index, n_index, stream)));
-    CU(static_cast<cudaError_t>(rs_launch_run(&a2, &c2, m.nlayers, 0, m.use_coupling, m.depth_mode != 0, stream, &li->grid, &li->block,
+    CU(static_cast<cudaError_t>(rs_launch_run(&a2, &c2, m.nlayers, 0, m.use_coupling, m.use_relaxation, m.depth_mode != 0, stream, &li->grid, &li->block,
                                               &li->regs_per_thread, &li->smem_bytes)));
   }
   CU(static_cast<cudaError_t>(rs_launch_partition(flags, a.ld, a.npoints, 1, index, n_index, stream)));
@@ -129,7 +129,7 @@ int launch_model(const RsArgs& a, const RsArgsCold& ac, const RsModel& m, int we
   a3.step_begin = wend + 1;
   c3.index = index;
   c3.n_index = n_index;
-  CU(static_cast<cudaError_t>(rs_launch_run(&a3, &c3, m.nlayers, 0, m.use_coupling, m.depth_mode != 0, stream, &li->grid, &li->block,
+  CU(static_cast<cudaError_t>(rs_launch_run(&a3, &c3, m.nlayers, 0, m.use_coupling, m.use_relaxation, m.depth_mode != 0, stream, &li->grid, &li->block,
                                             &li->regs_per_thread, &li->smem_bytes)));
   *launches = 2 * passes + 3;
   return RS_OK;
