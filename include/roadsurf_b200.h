@@ -507,6 +507,11 @@ void roadsurf_release_workspace(void);
  * "coupling_compaction_passes" (default 6, 0 = off): with RsDeviceBatch.coupling_window_end set, the
  * number of compacted passes over the coupling window before the points still iterating finish
  * inside the last launch.
+ * "write_back_inputs" (default 0): 1 = roadsurf_run_batch and runsimulation also leave the caller's INPUT arrays
+ * as the reference leaves them -- VZ[0] clamped to 0.4 (src/Initialization.f90:121-123), SW_dir[i] <= SW[i] for every
+ * visited step (src/InputOutput.f90:75-77) and, for sky-view points, SW / SW_dir / LW of every executed step rewritten
+ * by ModRadiationBySurroundings (src/ModRadiation.f90:57,65,70).  Neither example reads them after the call, so this is
+ * off by default (it costs one more pass over three planes); the header declares the inputs const like the examples do.
  * "max_points_per_device_batch": cap on the points roadsurf_run_batch puts into one device batch
  * (0 = bounded by free device memory only); batches beyond it are processed one after another. */
 int roadsurf_set_option(const char* name, int value);

@@ -52,6 +52,9 @@ std::atomic<int> g_opt_max_slots{0};  // test hook: cap on points per device bat
 // coupling_compaction_passes: number of compacted passes over the coupling window before the points
 // still iterating are left to finish inside the last launch (0 = one launch, warps repeat in place).
 std::atomic<int> g_opt_compaction{6};
+// write_back_inputs: roadsurf_run_batch / runsimulation also reproduce the reference's in-place mutation of the
+// caller's input arrays (VZ[0], SW_dir, and SW / SW_dir / LW of sky-view points).  Off by default.
+std::atomic<int> g_opt_write_back{0};
 int opt_compaction_passes() { return g_opt_compaction.load(); }
 int opt_staging()
 {
@@ -702,6 +705,35 @@ int run_shard(Shard& sh, OutputPointers* const* out, const InputPointers* const*
         const double t0 = now_ms();
         scatter(prev_q0, prev_npc, h_st[(cidx - 1) & 1]);
         os.unpack_ms += now_ms() - t0;
+      }
+      if (g_opt_write_back.load())
+      {
+        // the reference's caller-visible input mutations (see rs_mutation_kernel), chunk by chunk through the
+        // first staging buffer; VZ(1) is clamped on the host (src/Initialization.f90:121-123)
+        PooledDevice d_nvis;
+        CU(d_nvis.alloc(dv, 212 + (&c == &ctx[1] ? 50 : 0), sizeof(int) * ld));
+        for (int q0 = 0; q0 < ld; q0 += c.chunk)
+        {
+          const int npc = std::min(c.chunk, ld - q0);
+          const size_t plane = static_cast<size_t>(npc) * sim_len;
+          CU(static_cast<cudaError_t>(rs_launch_mutation(c.d_forcing.as<double>(), nvar, ld, sim_len, c.d_local.as<double>(),
+                                                         any_sky ? c.d_hor.as<double>() : nullptr, d_solar.as<double>(),
+                                                         c.d_out.as<double>(), d_nvis.as<int>(), q0, npc, d_st[0], st)));
+          os.kernel_launches += q0 == 0 ? 2 : 1;
+          CU(cudaMemcpyAsync(h_st[0], d_st[0], sizeof(double) * 3 * plane, cudaMemcpyDeviceToHost, st));
+          CU(cudaStreamSynchronize(st));
+          os.d2h_bytes += sizeof(double) * 3 * plane;
+          const double* S = h_st[0];
+          parallel_for(npc, nthreads, [&](int q) {
+            const int p = slots[s0 + q0 + q];
+            if (p < 0) return;
+            const InputPointers* ip = in[p];
+            double* dst[3] = {ip->c_SW, ip->c_SW_dir, ip->c_LW};
+            for (int v = 0; v < 3; ++v)
+              std::memcpy(dst[v], S + v * plane + static_cast<size_t>(q) * sim_len, sizeof(double) * sim_len);
+            if (ip->c_VZ[0] < 0.4f) ip->c_VZ[0] = 0.4f;
+          });
+        }
       }
       CU(cudaMemcpyAsync(c.h_status.p, c.d_status.p, sizeof(int) * ld, cudaMemcpyDeviceToHost, st));
       unsigned long long cnt[RS_CNT_N];
@@ -1729,6 +1761,11 @@ int roadsurf_set_option(const char* name, int value)
   if (name && std::strcmp(name, "coupling_compaction_passes") == 0)
   {
     g_opt_compaction = value > 0 ? (value > 30 ? 30 : value) : 0;
+    return RS_OK;
+  }
+  if (name && std::strcmp(name, "write_back_inputs") == 0)
+  {
+    g_opt_write_back = value ? 1 : 0;
     return RS_OK;
   }
   if (name && std::strcmp(name, "max_points_per_device_batch") == 0)

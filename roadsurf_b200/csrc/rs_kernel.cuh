@@ -56,6 +56,9 @@ enum
 // Host-callable launchers (rs_kernel.cu).  Return a cudaError_t as int.
 int rs_upload_model(const RsModel* m);
 int rs_launch_solar(const int* tf, int sim_len, double* table, void* stream);
+// write-back of the reference's input mutations: stage [3][npc][sim_len] = SW, SW_dir, LW as the reference leaves them
+int rs_launch_mutation(const double* forcing, int nvar, int ld, int sim_len, const double* local, const double* horizons,
+                       const double* solar, const double* tsurf_out, int* nvis, int q0, int npc, double* stage, void* stream);
 int rs_launch_sun_position(const int* tf, int n_steps, const double* lat, const double* lon, int npoints, double* elev,
                            double* azim, void* stream);
 // coarse records -> per-step forcing [step_end - step_begin + 1][nvar][ld]; rule 1 = example1, 2 = example2

@@ -1210,3 +1210,34 @@ def test_guard_planes_around_every_written_tensor_stay_intact(rslib):
         torch.cuda.synchronize()
         intact(bufs)
         assert (db.status[:npts] & rslib.ST_NOT_RUN).sum() == 0
+
+
+def test_opt_in_write_back_reproduces_the_references_input_mutations(rslib, oracle):
+    """The reference mutates its INPUT arrays (VZ(1) clamp, SW_dir <= SW per visited step, sky-view rewrite of
+    SW / SW_dir / LW per executed step, restored and re-applied by coupling re-runs).  With the option
+    "write_back_inputs" the caller's arrays after roadsurf_run_batch equal the oracle's after its run, bit for
+    bit; without it (the default) they are untouched."""
+    arrays, settings, params, _ = synth.make_case(200, 3, seed=380, analysis_hours=3, use_coupling=1, use_relaxation=1,
+                                                   sky_view_fraction=0.5, settings_kw=dict(coupling_minutes=60))
+    arrays.VZ[:50, 0] = 0.1                        # clamped to 0.4 by Initialization
+    arrays.SW_dir[:, 100:140] += 500.0             # above SW: clamped by CheckValues
+    arrays.tair[7, 300] = 500.0                    # point 7 fails at step 301: nothing after it is touched
+    ref, untouched = arrays.copy(), arrays.copy()
+    st_cpu, _ = oracle.run_batch(ref, settings, params, nthreads=8)
+    rslib.run_batch(untouched, settings, params)
+    for k in ("VZ", "SW", "SW_dir", "LW"):
+        assert np.array_equal(getattr(untouched, k), getattr(arrays, k)), k
+    rslib.set_option("write_back_inputs", 1)
+    try:
+        st = rslib.run_batch(arrays, settings, params)
+    finally:
+        rslib.set_option("write_back_inputs", 0)
+    assert np.array_equal(st, st_cpu)
+    for k in ref.out:
+        assert np.array_equal(arrays.out[k], ref.out[k], equal_nan=True), k
+    changed = 0
+    for k in ("VZ", "SW", "SW_dir", "LW", "tair", "LW_net", "prec"):
+        assert np.array_equal(getattr(arrays, k), getattr(ref, k), equal_nan=True), k
+        changed += int((getattr(arrays, k) != getattr(untouched, k)).sum())
+    assert changed > 1000
+    assert np.array_equal(arrays.SW_dir[7, 301:], untouched.SW_dir[7, 301:])      # beyond the failure: as given
