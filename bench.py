@@ -136,10 +136,12 @@ class ClockSampler(threading.Thread):
 class Workload:
     """One rank's share of a named configuration: a coarse-record device batch + how to step it."""
 
-    def __init__(self, args, rank, world, device):
+    def __init__(self, args, rank, world, device, data_only=False):
+        """data_only: generate the workload's data and nothing else (the reference arm: libroadsurf_b200.so is
+        never loaded there, torch is used for the random numbers only)."""
         import torch
         from roadsurf_b200 import abi, lib, synth, synth_torch
-        self.torch, self.lib = torch, lib
+        self.torch, self.lib, self.data_only = torch, lib, data_only
         w = WORKLOADS[args.workload]
         self.name, self.args = args.workload, args
         self.P = rank_points(args, world)
@@ -155,7 +157,8 @@ class Workload:
         else:
             self.settings = abi.default_settings(self.sim_len)
         self.params = abi.default_parameters(30.0)
-        lib.set_model(self.settings, self.params)
+        if not data_only:
+            lib.set_model(self.settings, self.params)
         self.db = lib.DeviceBatch(self.P, self.sim_len, n_records=nrec, coarse=True, horizons=True, out_stride=120,
                                   coupling=self.coupled, state=self.coupled)
         start = synth.FORECAST_START - __import__("datetime").timedelta(hours=self.analysis)
@@ -174,6 +177,8 @@ class Workload:
                                                                                dtype=torch.float64, device=db.forcing.device)
         obs[self.analysis + 1:] = -9999.9
         db.forcing[:, lib.F_NAMES.index("TSurfObs")] = obs
+        if self.data_only:
+            return                      # (cpu_case re-derives the per-point parameters on the host, in Python)
         forcing = db.forcing[:, :, :self.P].cpu().contiguous()
         local = db.local[:, :self.P].cpu().contiguous()
         forecast_step = self.analysis * 120
@@ -268,10 +273,8 @@ def run_reference(args):
     npts = args.cpu_sample_points
     world = max(1, args.gpus)
     if torch.cuda.is_available():
-        from roadsurf_b200 import build as rs_build
-        rs_build.build_library()
         torch.cuda.set_device(0)
-        wl = Workload(args, 0, world, torch.device("cuda", 0))
+        wl = Workload(args, 0, world, torch.device("cuda", 0), data_only=True)
         arrays, settings, params = wl.cpu_case(npts)
         source = "the first %d points of the GPU arm's rank-0 workload (same generator call, same seed)" % arrays.npoints
         del wl
@@ -517,10 +520,10 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world, {"kernel_regs": launch["regs_per_thread"], "grid": launch["grid"],
-                                                    "block": launch["block"], "bl_iterations_per_step": bl_per_step,
-                                                    "failed_points": failed_points,
-                                                    "executed_over_nominal_steps": executed_over_nominal}),
+            "config": workload_config(args, world),
+            "launch": {"kernel_regs": launch["regs_per_thread"], "grid": launch["grid"], "block": launch["block"],
+                       "bl_iterations_per_step": bl_per_step, "failed_points": failed_points,
+                       "executed_over_nominal_steps": executed_over_nominal},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
             "parity_sample": parity_sample, "full_config": full_config}
