@@ -7,8 +7,12 @@
 // with libm's own algorithm makes the CUDA path bit-identical to the CPU restatement wherever only
 // + - * / sqrt exp log are involved.
 //
-// Algorithm and tables: glibc sysdeps/ieee754/dbl-64/e_exp.c, e_log.c (ARM optimized-routines,
-// Szabolcs Nagy): table-driven, 128 entries each.  The ORDER OF OPERATIONS and the placement of the
+// PROVENANCE (third-party, not from the RoadSurf reference): the algorithm and the table / coefficient
+// data are those of the GNU C Library's double-precision exp and log, sysdeps/ieee754/dbl-64/e_exp.c,
+// e_log.c, e_exp_data.c, e_log_data.c -- contributed to glibc from ARM's optimized-routines (Szabolcs
+// Nagy; MIT OR Apache-2.0 WITH LLVM-exception upstream, LGPL-2.1-or-later as distributed in glibc).
+// rs_libm_tables.h holds numbers read out of the installed libm.so.6, this file re-expresses the
+// evaluation scheme; neither contains glibc source text.  Table-driven, 128 entries each.  The ORDER OF OPERATIONS and the placement of the
 // fused multiply-adds below are those of libm's __exp_fma / __log_fma as disassembled from the
 // libm.so.6 the tables come from (scripts/gen_libm_tables.py); tests/test_libm_match.py compares the
 // host build of this header with libm on 2e7 arguments.  Arguments outside the fast path (|x| >= 512
