@@ -43,6 +43,9 @@ struct RsArgsCold
   int n_fixed;
   int mode;                      // RS_MODE_* bits
   int window_end;                // RS_MODE_SPLIT: the coupling window end every coupled point must have
+  int tid0, tid_end;             // this launch covers the thread slots [tid0, tid_end) of the batch (0, 0 = all):
+                                 // a large grid is launched as whole waves of 512-thread blocks + a tail of
+                                 // 128-thread blocks spread over all SMs (see launch_sized)
 };
 
 enum
