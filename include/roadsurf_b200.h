@@ -384,7 +384,8 @@ typedef struct RsHostBatch
 {
   int npoints;
   int sim_len;
-  int forcing_mode;           /* 0: one record per model step, 1: coarse records */
+  int forcing_mode;           /* 0: one record per model step, 1: coarse records (example1's rule); mode 2 is
+                                 offered by the device entry only (RS_ERR_UNSUPPORTED here) */
   int n_records;
   int nvar;                   /* RS_F_NVAR or RS_F_NVAR_DEPTH */
   int out_stride;

@@ -1145,6 +1145,9 @@ int roadsurf_run_host_soa(const RsHostBatch* b, const InputSettings* settings, c
   if (b->npoints < 0 || b->sim_len < 1 || b->out_stride < 1) return fail(RS_ERR_BAD_ARGUMENT, "bad sizes");
   if (b->sim_len != settings->SimLen) return fail(RS_ERR_BAD_ARGUMENT, "batch sim_len != settings SimLen");
   if (b->nvar != RS_F_NVAR && b->nvar != RS_F_NVAR_DEPTH) return fail(RS_ERR_BAD_ARGUMENT, "nvar must be 11 or 12");
+  if (b->forcing_mode != 0 && b->forcing_mode != 1)
+    return fail(RS_ERR_UNSUPPORTED, "roadsurf_run_host_soa takes forcing_mode 0 or 1 (example2's rule, mode 2, is offered by "
+                                    "the device entry: roadsurf_run_device / roadsurf_expand_records)");
   if (b->forcing_mode == 0 ? b->n_records != b->sim_len : (b->n_records < 2 || !b->record_step))
     return fail(RS_ERR_BAD_ARGUMENT, "bad n_records / record_step for the forcing mode");
   if (b->npoints > 0 && (!b->forcing || !b->time_fields || !b->local || !b->out))

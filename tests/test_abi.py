@@ -143,3 +143,31 @@ def test_batch_entry_fails_loudly_without_a_gpu():
     arrays, settings, params, _ = synth.make_case(2, 1, seed=1)
     with pytest.raises(lib.RoadSurfError, match="no CUDA device"):
         lib.run_batch(arrays, settings, params)
+
+
+def test_new_entry_points_fail_loudly_without_a_gpu_and_validate_arguments():
+    """Sessions and prepared statics have no CPU path either; argument errors are reported before any device
+    work (these run on the CPU box)."""
+    import ctypes as C
+    import numpy as np
+    import pytest
+    from roadsurf_b200 import synth
+    handle = lib.load()
+    arrays, settings, params, rec = synth.make_case(2, 1, seed=1)
+    # example2's rule is a device-entry feature: the host-SoA entry says so instead of misreading the records
+    forcing = np.zeros((rec.nrec, 11, 2))
+    local = np.zeros((lib.L_NLOCAL, 2))
+    out = np.zeros((lib.O_NVAR, arrays.sim_len, 2))
+    hb = lib.RsHostBatch(npoints=2, sim_len=arrays.sim_len, forcing_mode=2, n_records=rec.nrec, nvar=11, out_stride=1,
+                         forcing=forcing.ctypes.data, record_step=rec.record_step.ctypes.data,
+                         time_fields=arrays.time.ctypes.data, local=local.ctypes.data, out=out.ctypes.data)
+    assert handle.roadsurf_run_host_soa(C.byref(hb), C.byref(settings), C.byref(params), 1) == -4   # RS_ERR_UNSUPPORTED
+    assert b"forcing_mode 0 or 1" in handle.roadsurf_last_error()
+    if handle.roadsurf_device_count() > 0:
+        return
+    with pytest.raises(lib.RoadSurfError, match="no CUDA device"):
+        lib.Session(arrays, settings, params)
+    with pytest.raises(lib.RoadSurfError, match="no CUDA device"):
+        lib.prepare_statics(local, None, ngpus=1)
+    # a stale / foreign handle is rejected, not dereferenced blindly
+    assert handle.roadsurf_session_done(None) < 0
