@@ -47,3 +47,55 @@ def test_second_restatement_layer_depths_and_sun():
     from roadsurf_b200 import abi
     pyoracle.load().oracle_layer_depths(15, z.ctypes.data_as(abi.c_double_p))
     assert np.array_equal(np.array(pt.Z[1:17]), z)
+
+
+CASES = [
+    # name, make_case kwargs, post-processing of (arrays, settings)
+    ("nlayers 4, fixed output depth", dict(npoints=2, hours=3, seed=41, nlayers=4, settings_kw=dict(tsurf_output_depth=0.05)), None),
+    ("nlayers 12, output depth below the grid", dict(npoints=2, hours=3, seed=42, nlayers=12,
+                                                     settings_kw=dict(tsurf_output_depth=50.0)), None),
+    ("nlayers 20, depth 0 = top layer", dict(npoints=2, hours=3, seed=43, nlayers=20, settings_kw=dict(tsurf_output_depth=0.0)), None),
+    ("per-step depth array", dict(npoints=2, hours=3, seed=44), "depth"),
+    ("force_tsurf with observations throughout", dict(npoints=2, hours=2, seed=45, analysis_hours=2,
+                                                      settings_kw=dict(force_tsurf=1)), "obs_everywhere"),
+    ("coupling with a short window, relaxation, sky view", dict(npoints=3, hours=2, seed=46, analysis_hours=2, use_coupling=1,
+                                                              use_relaxation=1, sky_view_fraction=1.0,
+                                                              settings_kw=dict(coupling_minutes=30)), None),
+    ("coupling whose window starts at step 1", dict(npoints=2, hours=1, seed=47, analysis_hours=1, use_coupling=1,
+                                                    settings_kw=dict(coupling_minutes=600)), None),
+    ("bad input in the middle, NaN input", dict(npoints=3, hours=2, seed=48), "bad"),
+    ("summer day with shadows (sun well above the horizon)", dict(npoints=3, hours=6, seed=49, sky_view_fraction=1.0), "summer"),
+]
+
+
+@pytest.mark.parametrize("name,kw,post", CASES, ids=[c[0] for c in CASES])
+def test_two_restatements_agree_on_the_odd_paths(oracle, name, kw, post):
+    """The same N-version check on the paths the golden cases do not take: other layer counts, the output
+    depth variants, forced surface temperature, short / clipped coupling windows, failing and NaN inputs,
+    a high sun."""
+    import datetime as dt
+    from roadsurf_b200 import synth
+    if post == "summer":
+        kw = dict(kw, start=dt.datetime(2019, 6, 21, 3, 0, 0))
+    arrays, settings, params, rec = synth.make_case(**kw)
+    if post == "depth":
+        arrays.Depth[0, :] = 0.03
+        arrays.Depth[1, ::2] = 0.5
+    if post == "obs_everywhere":
+        arrays.TSurfObs[:, :] = arrays.tair - 0.7
+    if post == "bad":
+        arrays.VZ[0, 100] = 250.0
+        arrays.tair[1, 50] = float("nan")
+        arrays.PrecPhase[2, :] = 9          # an unknown phase code: falls back to the interpretation
+    ref = arrays.copy()
+    st, executed = oracle.run_batch(ref, settings, params, nthreads=1)
+    total = 0
+    for p in range(arrays.npoints):
+        out, nsteps, failed = py_restatement.run_point(arrays, settings, params, p)
+        total += nsteps
+        assert failed == bool(st[p] & 1), (name, p)
+        for k, v in out.items():
+            assert np.array_equal(np.isnan(v), np.isnan(ref.out[k][p])), (name, p, k)
+            d = np.abs(v - ref.out[k][p])
+            assert not (np.nanmax(d) >= 1e-9), (name, p, k, int(np.nanargmax(d)), float(np.nanmax(d)))
+    assert total == executed, name
