@@ -88,15 +88,15 @@ def test_file_pipeline_on_the_gpu_matches_the_cpu_model(tmp_path, rslib, oracle)
     assert [s["statId"] for s in f_gpu] == [s["statId"] for s in f_cpu]
 
 
-def _build_cpp_example(tmp_path):
+def _build_cpp_example(tmp_path, name="batch_main"):
     import os, subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     from roadsurf_b200 import build
     build.build_library()
-    exe = str(tmp_path / "batch_main")
+    exe = str(tmp_path / name)
     libdir = os.path.join(root, "roadsurf_b200")
     subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
-                    os.path.join(root, "examples", "batch_main.cpp"), "-o", exe, "-L", libdir, "-lroadsurf_b200",
+                    os.path.join(root, "examples", name + ".cpp"), "-o", exe, "-L", libdir, "-lroadsurf_b200",
                     "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
     return exe
 
@@ -123,3 +123,27 @@ def test_cpp_example_main_runs_a_coupled_batch(tmp_path):
     r = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "coupled points 200, failed 0" in r.stdout, r.stdout
+
+
+def test_cpp_stepwise_main_builds_and_reports_a_missing_gpu(tmp_path):
+    """examples/step_main.cpp: a main that keeps its own time loop over the step-granular entry points (what the
+    Fortran module RoadSurf forwards to) compiles with -Wall -Werror and, without a GPU, says so."""
+    import subprocess
+    import torch
+    exe = _build_cpp_example(tmp_path, "step_main")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert "1 point x 481 steps" in r.stdout, r.stdout + r.stderr
+    if not torch.cuda.is_available():
+        assert r.returncode == 0 and "no CUDA device visible" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_stepwise_main_equals_runsimulation(tmp_path):
+    """The stepwise main on a GPU, one launch per step and with a run-ahead chunk: every output value equals
+    runsimulation's (exit code 0)."""
+    import subprocess
+    exe = _build_cpp_example(tmp_path, "step_main")
+    for chunk in ("1", "60"):
+        r = subprocess.run([exe, chunk], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "values differing from runsimulation: 0" in r.stdout, r.stdout
