@@ -6,12 +6,19 @@
 // roadsurf_read_input_derive exactly where the reference calls read_input, runs the batch and prints
 // a few values.  Without a CUDA device it reports that and exits 0 (the library has no CPU path).
 //
-//   g++ -std=c++17 -O2 -I include examples/batch_main.cpp -o batch_main -L roadsurf_b200 -lroadsurf_b200
+// With a second argument T > 0 the same points then go through the reference's own entry `runsimulation`,
+// one point per call from a pool of T threads -- the shape of the reference's main
+// (examples/example1/src/roadrunner.cpp:454-496) -- and the two result sets are compared value by value.
+//
+//   g++ -std=c++17 -O2 -pthread -I include examples/batch_main.cpp -o batch_main -L roadsurf_b200 -lroadsurf_b200
 //   (plus -Wl,-rpath,<repo>/roadsurf_b200 or LD_LIBRARY_PATH)
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "roadsurf_b200.h"
@@ -29,6 +36,7 @@ struct PointData  // the vectors the reference keeps in InputData / OutputData (
 int main(int argc, char** argv)
 {
   const int npoints = argc > 1 ? std::atoi(argv[1]) : 64;
+  const int pool_threads = argc > 2 ? std::atoi(argv[2]) : 0;
   const int analysis_h = 3, forecast_h = 6;
   const double DT = 30.0;
   const int per_hour = static_cast<int>(3600.0 / DT);
@@ -124,12 +132,52 @@ int main(int argc, char** argv)
     return 0;
   }
   std::vector<int> status(npoints, 0);
+  using clock = std::chrono::steady_clock;
+  auto ms_since = [](clock::time_point t0) { return std::chrono::duration<double, std::milli>(clock::now() - t0).count(); };
+  roadsurf_device_count();
+  auto t0 = clock::now();
   const int rc = roadsurf_run_batch(npoints, out_ptr.data(), in_ptr.data(), &settings, &params, loc_cptr.data(), 1,
                                     status.data());
   if (rc != RS_OK)
   {
     std::fprintf(stderr, "run failed (%d): %s\n", rc, roadsurf_last_error());
     return 1;
+  }
+  const double batch_ms = ms_since(t0);
+  if (pool_threads > 0)
+  {
+    // the reference's way: a pool of host threads, each taking the next point and calling runsimulation on it
+    std::vector<std::vector<double>> o2(static_cast<size_t>(npoints) * 6, std::vector<double>(sim_len, -9999.0));
+    std::vector<OutputPointers> out2(npoints);
+    for (int p = 0; p < npoints; ++p)
+    {
+      out2[p].outputLen = sim_len;
+      out2[p].c_TsurfOut = o2[6 * p + 0].data(); out2[p].c_SnowOut = o2[6 * p + 1].data();
+      out2[p].c_WaterOut = o2[6 * p + 2].data(); out2[p].c_IceOut = o2[6 * p + 3].data();
+      out2[p].c_DepositOut = o2[6 * p + 4].data(); out2[p].c_Ice2Out = o2[6 * p + 5].data();
+    }
+    long long calls0 = 0, batches0 = 0, calls1 = 0, batches1 = 0;
+    roadsurf_runsimulation_counters(&calls0, &batches0);
+    std::atomic<int> next{0};
+    t0 = clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < pool_threads; ++t)
+      pool.emplace_back([&] {
+        for (int p = next++; p < npoints; p = next++) runsimulation(&out2[p], &in[p], &settings, &params, &local[p]);
+      });
+    for (auto& th : pool) th.join();
+    const double pool_ms = ms_since(t0);
+    roadsurf_runsimulation_counters(&calls1, &batches1);
+    long differing = 0;
+    for (int p = 0; p < npoints; ++p)
+    {
+      const std::vector<double>* a[6] = {&pts[p].Tsurf, &pts[p].Snow, &pts[p].Water, &pts[p].Ice, &pts[p].Deposit, &pts[p].Ice2};
+      for (int v = 0; v < 6; ++v) differing += std::memcmp(a[v]->data(), o2[6 * p + v].data(), sizeof(double) * sim_len) != 0;
+    }
+    std::printf("one roadsurf_run_batch: %.1f ms; runsimulation from %d threads: %.1f ms in %lld launches-batches for %lld calls; "
+                "series differing: %ld\n",
+                batch_ms, pool_threads, pool_ms, batches1 - batches0, calls1 - calls0, differing);
+    if (differing) return 3;
   }
   int coupled = 0, failed = 0;
   for (int p = 0; p < npoints; ++p)

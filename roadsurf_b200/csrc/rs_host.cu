@@ -2036,6 +2036,8 @@ std::mutex g_call_mu;
 std::condition_variable g_call_cv;
 std::vector<PendingCall*> g_call_queue;
 bool g_call_leader = false;
+size_t g_call_last_n = 0;     // calls in the last batch (0 = no batch yet); guarded by g_call_mu
+double g_call_last_ms = 0.0;  // wall time of the last batch
 std::atomic<long long> g_calls_total{0}, g_call_batches_total{0};
 
 void mark_not_computed(OutputPointers* outPointers, const InputSettings* inSettings)
@@ -2092,16 +2094,35 @@ extern "C" void runsimulation(OutputPointers* outPointers, const InputPointers* 
     }
     // become the leader for ONE batch: everything queued with the same settings and parameters as this call
     g_call_leader = true;
-    // callers of a thread pool arrive together (and come back together after a batch): give them a moment
-    // to queue up -- at least 1 ms, up to 5 ms while the queue keeps growing, against a run of ~100 ms whatever
-    // the batch size -- so that a batch holds the whole pool and not its first arrival
+    // Callers of a thread pool come back together after a batch, staggered by whatever each does between two
+    // calls (reading the next point, writing the last one out).  A batch costs about the same whatever its
+    // size, so the leader waits for the pool to queue up again: until as many calls wait as the last batch
+    // held, bounded by a fifth of the last batch's run time (1..20 ms).  With no history (first batch) or a
+    // lone caller (last batch of 1) the bound is: at least 1 ms resp. no wait at all, and stop once the queue
+    // has not grown for 1 ms.
     {
-      size_t seen = g_call_queue.size();
-      for (int k = 0; k < 10; ++k)
+      using clock = std::chrono::steady_clock;
+      const size_t expected = g_call_last_n;
+      if (expected != 1)
       {
-        g_call_cv.wait_for(lk, std::chrono::microseconds(500), [] { return false; });
-        if (k >= 1 && g_call_queue.size() == seen) break;
-        seen = g_call_queue.size();
+        const double budget_ms = std::min(20.0, std::max(1.0, 0.2 * g_call_last_ms));
+        const auto t0 = clock::now();
+        auto last_growth = t0;
+        size_t seen = g_call_queue.size();
+        while (g_call_queue.size() < expected || expected == 0)
+        {
+          g_call_cv.wait_for(lk, std::chrono::microseconds(250), [] { return false; });
+          const auto now = clock::now();
+          if (g_call_queue.size() != seen)
+          {
+            seen = g_call_queue.size();
+            last_growth = now;
+          }
+          const double waited = std::chrono::duration<double, std::milli>(now - t0).count();
+          const double idle = std::chrono::duration<double, std::milli>(now - last_growth).count();
+          if (waited >= budget_ms) break;
+          if (expected == 0 && waited >= 1.0 && idle >= 1.0) break;
+        }
       }
     }
     std::vector<PendingCall*> batch, rest;
@@ -2125,9 +2146,12 @@ extern "C" void runsimulation(OutputPointers* outPointers, const InputPointers* 
       ins[k] = batch[k]->in;
       locs[k] = batch[k]->local;
     }
+    const auto run_t0 = std::chrono::steady_clock::now();
     const int rc = roadsurf_run_batch(n, outs.data(), ins.data(), me.settings, me.params, locs.data(), 1, nullptr);
     const std::string err = (rc != RS_OK) ? std::string(roadsurf_last_error()) : std::string();
     lk.lock();
+    g_call_last_n = static_cast<size_t>(n);
+    g_call_last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - run_t0).count();
     for (PendingCall* c : batch)
     {
       c->rc = rc;

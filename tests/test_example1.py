@@ -95,7 +95,7 @@ def _build_cpp_example(tmp_path, name="batch_main"):
     build.build_library()
     exe = str(tmp_path / name)
     libdir = os.path.join(root, "roadsurf_b200")
-    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+    subprocess.run(["g++", "-std=c++17", "-O2", "-pthread", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
                     os.path.join(root, "examples", name + ".cpp"), "-o", exe, "-L", libdir, "-lroadsurf_b200",
                     "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
     return exe
@@ -147,3 +147,18 @@ def test_cpp_stepwise_main_equals_runsimulation(tmp_path):
         r = subprocess.run([exe, chunk], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout + r.stderr
         assert "values differing from runsimulation: 0" in r.stdout, r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_thread_pool_of_runsimulation_calls_is_batched(tmp_path):
+    """The reference's main shape (roadrunner.cpp:454-496): a pool of 16 threads, one runsimulation call per point.
+    The calls are combined into batches of about the pool size, and every series equals the one-batch run."""
+    import re, subprocess
+    exe = _build_cpp_example(tmp_path)
+    r = subprocess.run([exe, "200", "16"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"in (\d+) launches-batches for (\d+) calls; series differing: (\d+)", r.stdout)
+    assert m, r.stdout
+    batches, calls, differing = map(int, m.groups())
+    assert calls == 200 and differing == 0
+    assert batches <= 40, r.stdout          # 200 / 16 = 12.5 ideal; one call per launch would be 200
