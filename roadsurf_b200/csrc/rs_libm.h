@@ -40,6 +40,27 @@ __device__ const double __align__(16) d_log_tab[256] = RS_LIBM_LOG_TAB;         
 #endif
 static const unsigned long long h_exp_tab[256] = RS_LIBM_EXP_TAB;
 static const double h_log_tab[256] = RS_LIBM_LOG_TAB;
+// RS_TABLES_SMEM = 1: a kernel that evaluates exp / log copies both tables (4 KB) into shared memory first
+// (stage_tables, all threads of the block, before any of them exits) and the lookups are LDS.128: ~30 cycles
+// instead of an L1 (~40) or L2 (~250) access, which a warp that is alone on its scheduler waits out in full
+#ifndef RS_TABLES_SMEM
+#define RS_TABLES_SMEM 0
+#endif
+#if defined(__CUDACC__) && RS_TABLES_SMEM
+__shared__ ulonglong2 s_exp_tab[128];
+__shared__ double2 s_log_tab[128];
+__device__ __forceinline__ void stage_tables()
+{
+  for (unsigned k = threadIdx.x; k < 128u; k += blockDim.x)
+  {
+    s_exp_tab[k] = __ldg(reinterpret_cast<const ulonglong2*>(d_exp_tab) + k);
+    s_log_tab[k] = __ldg(reinterpret_cast<const double2*>(d_log_tab) + k);
+  }
+  __syncthreads();
+}
+#elif defined(__CUDACC__)
+__device__ __forceinline__ void stage_tables() {}
+#endif
 // scalar coefficients: on the device operands from the constant bank (as literals each costs two
 // move instructions per use and the functions are inlined at several sites), on the host literals
 #if defined(__CUDACC__)
@@ -104,7 +125,11 @@ RS_LIBM_HD double asd(uint64_t u)
 }
 RS_LIBM_HD void exp_entry(uint32_t i, double& tail, uint64_t& sbits)
 {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && RS_TABLES_SMEM
+  const ulonglong2 e = s_exp_tab[i];
+  tail = asd(e.x);
+  sbits = e.y;
+#elif defined(__CUDA_ARCH__)
   const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2*>(d_exp_tab) + i);
   tail = asd(e.x);
   sbits = e.y;
@@ -115,7 +140,11 @@ RS_LIBM_HD void exp_entry(uint32_t i, double& tail, uint64_t& sbits)
 }
 RS_LIBM_HD void log_entry(uint32_t i, double& invc, double& logc)
 {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && RS_TABLES_SMEM
+  const double2 e = s_log_tab[i];
+  invc = e.x;
+  logc = e.y;
+#elif defined(__CUDA_ARCH__)
   const double2 e = __ldg(reinterpret_cast<const double2*>(d_log_tab) + i);
   invc = e.x;
   logc = e.y;
