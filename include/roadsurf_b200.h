@@ -194,6 +194,10 @@ int roadsurf_run_batch(int npoints, OutputPointers* const* out, const InputPoint
  *   - with use_coupling == 1: the latest valid TSurfObs index i (not NaN, >= -100); if
  *     i >= coupling_minutes*60/DTSecs: couplingTsurf = TSurfObs[i], couplingIndexI = i and
  *     TSurfObs is blanked to -9999.9 over (i - span, i] IN THE CALLER'S ARRAY, as read_input does.
+ * example2's read_input (examples/example2/src/roadrunner.cpp:139-264) is the same function with one
+ * difference in the relaxation block: from the time of the latest air-temperature observation it sets
+ * InitLenI = secs/DTSecs + 1 and takes the targets at the 0-based index InitLenI (:223-231) -- pass
+ * latest_obs_index[p] = secs/DTSecs + 1 and the two coincide (tests/test_host_logic.py).
  * latest_obs_index and ok may be NULL.  Pure host code: works without a GPU.  Returns RS_OK. */
 int roadsurf_read_input_derive(int npoints, const InputPointers* const* in, const InputSettings* settings,
                                int forecast_step, const int* latest_obs_index, LocalParameters* const* local,

@@ -1335,7 +1335,7 @@ int roadsurf_session_open(int npoints, OutputPointers* const* out, const InputPo
                                      static_cast<double>(lp.InitLenI), 1.0};
     for (int k = 0; k < RS_L_NLOCAL; ++k) hl[k * ld + p] = row[k];
     if (any_sky)
-      for (int k = 0; k < 360; ++k) hh[static_cast<size_t>(k) * ld + p] = ip->c_local_horizons[k];
+      for (int k = 0; k < 360; ++k) hh[static_cast<size_t>(k) * ld + p] = ip->c_local_horizons ? ip->c_local_horizons[k] : 0.0;
     s->outs[p] = *out[p];
     double* o[RS_O_NVAR] = {out[p]->c_TsurfOut, out[p]->c_SnowOut,    out[p]->c_WaterOut,
                             out[p]->c_IceOut,   out[p]->c_DepositOut, out[p]->c_Ice2Out};

@@ -322,3 +322,42 @@ def _short_records(rec, cut):
         setattr(short, v, getattr(rec, v)[:, :rec.nrec - cut].copy())
     short.record_step = rec.record_step[:rec.nrec - cut]
     return short
+
+
+def test_read_input_derive_covers_example2s_relaxation_rule():
+    """example2's read_input (examples/example2/src/roadrunner.cpp:139-264) differs from example1's only in the
+    relaxation block: InitLenI = secs/DT + 1 from the TIME of the latest air-temperature observation, targets at
+    the 0-based index InitLenI (:223-231).  Restated here directly and compared with the library called the way
+    the header says (latest_obs_index = secs/DT + 1), point by point, with per-point observation times."""
+    from roadsurf_b200 import lib
+    rng = np.random.default_rng(5)
+    arrays, settings, params, rec = synth.make_case(24, 6, seed=11, analysis_hours=6, use_coupling=1, use_relaxation=1)
+    raw, _, _ = synth.case_from_records(rec, 6, 6, 0, 0)
+    dt, sim_len = settings.DTSecs, settings.SimLen
+    forecast_step = 720
+    obs_secs = rng.integers(3 * 3600, 6 * 3600, size=24) // 30 * 30      # seconds after start_time, per point
+    obs_secs[7] = -1                                                      # a point without air-temperature observations
+    span = int(settings.coupling_minutes * 60 / dt)
+    want = []
+    for p in range(24):
+        init_len = 1 + int(forecast_step * dt / dt)                       # :162-164
+        tr = vr = rr = -9999.9
+        if obs_secs[p] >= 0:                                              # :220-231
+            init_len = int(obs_secs[p] / dt) + 1
+            tr, vr, rr = raw.tair[p, init_len], raw.VZ[p, init_len], raw.Rhz[p, init_len]
+        obs = raw.TSurfObs[p]
+        i = sim_len - 1                                                   # :234-259
+        while i >= 0 and (np.isnan(obs[i]) or obs[i] < -9000 or obs[i] < -100):
+            i -= 1
+        ci, ct = -9999, -9999.9
+        if i >= span:
+            ci, ct = i, obs[i]
+        want.append((init_len, tr, vr, rr, ci, ct))
+    idx = np.where(obs_secs >= 0, obs_secs // 30 + 1, -1).astype(np.int32)
+    ok = lib.read_input_derive(raw, settings, forecast_step, latest_obs_index=idx)
+    assert ok.all()
+    for p in range(24):
+        lp = raw.local[p]
+        assert (lp.InitLenI, lp.tair_relax, lp.VZ_relax, lp.RH_relax, lp.couplingIndexI, lp.couplingTsurf) == want[p], p
+        if want[p][4] > 0:                                                # blanked over (i - span, i]
+            assert (raw.TSurfObs[p, want[p][4] - span + 1: want[p][4] + 1] == -9999.9).all()
