@@ -188,6 +188,37 @@ RS_LIBM_HD double exp_fast(double x, bool& ok)
   return fma_(scale, tmp, scale);
 }
 
+// exp_fast without branches (same operations, same results): every lane evaluates the main path, the
+// |x| < 2^-54 case is a select and arguments outside the fast path only clear `ok`.  For call sites that
+// are to stay inside one basic block.
+RS_LIBM_HD double exp_fast_flat(double x, bool& ok)
+{
+  const uint32_t abstop = static_cast<uint32_t>(asu(x) >> 52) & 0x7ff;
+  const bool tiny = abstop < 0x3c9u;
+  ok = tiny || (abstop - 0x3c9u <= 0x3eu);
+  const double InvLn2N = RS_EK(0), Shift = RS_EK(1);
+  const double NegLn2hiN = RS_EK(2), NegLn2loN = RS_EK(3);
+  const double C2 = RS_EK(4), C3 = RS_EK(5), C4 = RS_EK(6), C5 = RS_EK(7);
+  double kd = fma_(x, InvLn2N, Shift);
+  const uint64_t ki = asu(kd);
+  kd = add_(kd, -Shift);
+  const double r = fma_(kd, NegLn2loN, fma_(kd, NegLn2hiN, x));
+  double tail;
+  uint64_t sbits;
+  exp_entry(static_cast<uint32_t>(ki & 127u), tail, sbits);
+  sbits += ki << 45;
+  const double p23 = fma_(r, C3, C2);
+  const double tr = add_(r, tail);
+  const double r2 = mul_(r, r);
+  const double p45 = fma_(r, C5, C4);
+  const double t1 = fma_(p23, r2, tr);
+  const double r4 = mul_(r2, r2);
+  const double tmp = fma_(r4, p45, t1);
+  const double scale = asd(sbits);
+  const double y = fma_(scale, tmp, scale);
+  return tiny ? add_(1.0, x) : y;
+}
+
 // log(x).  `ok` is false for x <= 0, subnormal, inf, NaN.
 RS_LIBM_HD double log_fast(double x, bool& ok)
 {
