@@ -517,6 +517,11 @@ void roadsurf_release_workspace(void);
  * visited step (src/InputOutput.f90:75-77) and, for sky-view points, SW / SW_dir / LW of every executed step rewritten
  * by ModRadiationBySurroundings (src/ModRadiation.f90:57,65,70).  Neither example reads them after the call, so this is
  * off by default (it costs one more pass over three planes); the header declares the inputs const like the examples do.
+ * "latency_body" (default -1): the step kernel exists in two bodies with identical results -- the throughput body,
+ * and a latency body for launches so small that every warp is alone on its scheduler (exp / log tables in shared
+ * memory, the saturation-pressure exponentials evaluated in the shadow of the boundary-layer divisions, no register
+ * cap).  -1 = the latency body for grids of at most one 128-thread block per SM, 0 = never, 1 = for every launch of
+ * 128-thread blocks.
  * "max_points_per_device_batch": cap on the points roadsurf_run_batch puts into one device batch
  * (0 = bounded by free device memory only); batches beyond it are processed one after another. */
 int roadsurf_set_option(const char* name, int value);

@@ -70,6 +70,7 @@ int rs_launch_expand(const double* rec, const int* record_step, int n_records, i
 int rs_launch_partition(const double* flags_plane, int ld, int npoints, int sorted, int* index, int* n_index, void* stream);
 // `coupling`: the model has use_coupling set; `depth`: it has a fixed output depth (depth_mode != 0).  Both select
 // the kernel variant compiled with exactly the features the run needs.
+void rs_set_latency_body(int mode);  // -1 auto (small grids), 0 never, 1 every 128-thread launch
 int rs_launch_run(const RsArgs* a, const RsArgsCold* cold, int nlayers, int staged, int coupling, int relaxation, int depth,
                   void* stream, int* grid, int* block, int* regs, int* smem);
 int rs_launch_transpose_to_soa(const double* src, long long src_ld, int npoints, int n, double* dst,

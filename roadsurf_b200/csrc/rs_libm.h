@@ -40,13 +40,12 @@ __device__ const double __align__(16) d_log_tab[256] = RS_LIBM_LOG_TAB;         
 #endif
 static const unsigned long long h_exp_tab[256] = RS_LIBM_EXP_TAB;
 static const double h_log_tab[256] = RS_LIBM_LOG_TAB;
-// RS_TABLES_SMEM = 1: a kernel that evaluates exp / log copies both tables (4 KB) into shared memory first
-// (stage_tables, all threads of the block, before any of them exits) and the lookups are LDS.128: ~30 cycles
-// instead of an L1 (~40) or L2 (~250) access, which a warp that is alone on its scheduler waits out in full
-#ifndef RS_TABLES_SMEM
-#define RS_TABLES_SMEM 0
-#endif
-#if defined(__CUDACC__) && RS_TABLES_SMEM
+// Shared-memory copies of the two tables for kernels that ask for them (template argument SMT = true on
+// the functions below): the block copies both tables (4 KB) first (stage_tables, all threads of the block,
+// before any of them exits) and the lookups are LDS.128, ~30 cycles instead of an L1 (~40) or L2 (~250)
+// access -- which a warp that is alone on its scheduler waits out in full.  Kernels that do not reference
+// the arrays allocate nothing.
+#if defined(__CUDACC__)
 __shared__ ulonglong2 s_exp_tab[128];
 __shared__ double2 s_log_tab[128];
 __device__ __forceinline__ void stage_tables()
@@ -58,8 +57,6 @@ __device__ __forceinline__ void stage_tables()
   }
   __syncthreads();
 }
-#elif defined(__CUDACC__)
-__device__ __forceinline__ void stage_tables() {}
 #endif
 // scalar coefficients: on the device operands from the constant bank (as literals each costs two
 // move instructions per use and the functions are inlined at several sites), on the host literals
@@ -123,14 +120,15 @@ RS_LIBM_HD double asd(uint64_t u)
   return x;
 #endif
 }
+template <bool SMT = false>
 RS_LIBM_HD void exp_entry(uint32_t i, double& tail, uint64_t& sbits)
 {
-#if defined(__CUDA_ARCH__) && RS_TABLES_SMEM
-  const ulonglong2 e = s_exp_tab[i];
-  tail = asd(e.x);
-  sbits = e.y;
-#elif defined(__CUDA_ARCH__)
-  const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2*>(d_exp_tab) + i);
+#if defined(__CUDA_ARCH__)
+  ulonglong2 e;
+  if constexpr (SMT)
+    e = s_exp_tab[i];
+  else
+    e = __ldg(reinterpret_cast<const ulonglong2*>(d_exp_tab) + i);
   tail = asd(e.x);
   sbits = e.y;
 #else
@@ -138,14 +136,15 @@ RS_LIBM_HD void exp_entry(uint32_t i, double& tail, uint64_t& sbits)
   sbits = h_exp_tab[2 * i + 1];
 #endif
 }
+template <bool SMT = false>
 RS_LIBM_HD void log_entry(uint32_t i, double& invc, double& logc)
 {
-#if defined(__CUDA_ARCH__) && RS_TABLES_SMEM
-  const double2 e = s_log_tab[i];
-  invc = e.x;
-  logc = e.y;
-#elif defined(__CUDA_ARCH__)
-  const double2 e = __ldg(reinterpret_cast<const double2*>(d_log_tab) + i);
+#if defined(__CUDA_ARCH__)
+  double2 e;
+  if constexpr (SMT)
+    e = s_log_tab[i];
+  else
+    e = __ldg(reinterpret_cast<const double2*>(d_log_tab) + i);
   invc = e.x;
   logc = e.y;
 #else
@@ -155,6 +154,7 @@ RS_LIBM_HD void log_entry(uint32_t i, double& invc, double& logc)
 }
 
 // exp(x).  `ok` is false when x is outside the fast path; the caller then uses its fallback.
+template <bool SMT = false>
 RS_LIBM_HD double exp_fast(double x, bool& ok)
 {
   const uint32_t abstop = static_cast<uint32_t>(asu(x) >> 52) & 0x7ff;
@@ -175,7 +175,7 @@ RS_LIBM_HD double exp_fast(double x, bool& ok)
   const double r = fma_(kd, NegLn2loN, fma_(kd, NegLn2hiN, x));
   double tail;
   uint64_t sbits;
-  exp_entry(static_cast<uint32_t>(ki & 127u), tail, sbits);
+  exp_entry<SMT>(static_cast<uint32_t>(ki & 127u), tail, sbits);
   sbits += ki << 45;
   const double p23 = fma_(r, C3, C2);
   const double tr = add_(r, tail);
@@ -191,6 +191,7 @@ RS_LIBM_HD double exp_fast(double x, bool& ok)
 // exp_fast without branches (same operations, same results): every lane evaluates the main path, the
 // |x| < 2^-54 case is a select and arguments outside the fast path only clear `ok`.  For call sites that
 // are to stay inside one basic block.
+template <bool SMT = false>
 RS_LIBM_HD double exp_fast_flat(double x, bool& ok)
 {
   const uint32_t abstop = static_cast<uint32_t>(asu(x) >> 52) & 0x7ff;
@@ -205,7 +206,7 @@ RS_LIBM_HD double exp_fast_flat(double x, bool& ok)
   const double r = fma_(kd, NegLn2loN, fma_(kd, NegLn2hiN, x));
   double tail;
   uint64_t sbits;
-  exp_entry(static_cast<uint32_t>(ki & 127u), tail, sbits);
+  exp_entry<SMT>(static_cast<uint32_t>(ki & 127u), tail, sbits);
   sbits += ki << 45;
   const double p23 = fma_(r, C3, C2);
   const double tr = add_(r, tail);
@@ -220,6 +221,7 @@ RS_LIBM_HD double exp_fast_flat(double x, bool& ok)
 }
 
 // log(x).  `ok` is false for x <= 0, subnormal, inf, NaN.
+template <bool SMT = false>
 RS_LIBM_HD double log_fast(double x, bool& ok)
 {
   const uint64_t ix = asu(x);
@@ -262,7 +264,7 @@ RS_LIBM_HD double log_fast(double x, bool& ok)
   const int k = static_cast<int>(static_cast<int64_t>(tmp) >> 52);
   const uint64_t iz = ix - (tmp & 0xfff0000000000000ull);
   double invc, logc;
-  log_entry(i, invc, logc);
+  log_entry<SMT>(i, invc, logc);
   const double z = asd(iz);
   const double kd = static_cast<double>(k);
   const double Ln2hi = RS_LK(0), Ln2lo = RS_LK(1);

@@ -1241,3 +1241,23 @@ def test_opt_in_write_back_reproduces_the_references_input_mutations(rslib, orac
         changed += int((getattr(arrays, k) != getattr(untouched, k)).sum())
     assert changed > 1000
     assert np.array_equal(arrays.SW_dir[7, 301:], untouched.SW_dir[7, 301:])      # beyond the failure: as given
+
+
+def test_latency_body_and_throughput_body_give_identical_results(rslib, oracle):
+    """The step kernel has two bodies (option "latency_body"): grids of at most one block per SM run the latency
+    body by default.  Both, forced in turn on the same coupled + sky-view case, must equal the oracle bit for bit --
+    so neither body is only covered by the grid sizes the other tests happen to use."""
+    arrays, settings, params, _ = synth.make_case(300, 12, seed=77, analysis_hours=6, use_coupling=1, use_relaxation=1)
+    ref = arrays.copy()
+    st_ref, _ = oracle.run_batch(ref, settings, params, nthreads=8)
+    try:
+        for mode in (0, 1, -1):
+            rslib.set_option("latency_body", mode)
+            work = arrays.copy()
+            st = rslib.run_batch(work, settings, params)
+            assert np.array_equal(st, st_ref), mode
+            _assert_parity(compare(work.out, ref.out))
+            regs = rslib.last_launch()["regs_per_thread"]
+            assert (regs > 168) == (mode != 0), (mode, regs)      # the latency body has no register cap
+    finally:
+        rslib.set_option("latency_body", -1)
