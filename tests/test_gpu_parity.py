@@ -1261,3 +1261,16 @@ def test_latency_body_and_throughput_body_give_identical_results(rslib, oracle):
             assert (regs > 168) == (mode != 0), (mode, regs)      # the latency body has no register cap
     finally:
         rslib.set_option("latency_body", -1)
+
+
+def test_other_time_steps_are_bit_identical_too(rslib, oracle):
+    """DTSecs enters the per-run constants (layer update factors, correctly rounded reciprocals, the coupling span,
+    wear and evaporation per step): 60 s and 20 s, with and without coupling / relaxation, against the oracle."""
+    for dt, kw in ((60.0, dict(analysis_hours=3, use_coupling=1, use_relaxation=1, settings_kw=dict(coupling_minutes=60))),
+                   (20.0, dict()),
+                   (120.0, dict(analysis_hours=2, use_relaxation=1))):
+        arrays, settings, params, _ = synth.make_case(96, 6, seed=int(dt), dt=dt, **kw)
+        assert settings.DTSecs == dt
+        r, st_gpu, st_cpu, _, _ = _run_both(rslib, oracle, arrays, settings, params)
+        _assert_parity(r)
+        assert np.array_equal(st_gpu, st_cpu), dt

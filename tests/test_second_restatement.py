@@ -65,6 +65,9 @@ CASES = [
                                                     settings_kw=dict(coupling_minutes=600)), None),
     ("bad input in the middle, NaN input", dict(npoints=3, hours=2, seed=48), "bad"),
     ("summer day with shadows (sun well above the horizon)", dict(npoints=3, hours=6, seed=49, sky_view_fraction=1.0), "summer"),
+    ("time step 60 s, coupling + relaxation", dict(npoints=2, hours=3, seed=50, analysis_hours=3, use_coupling=1, use_relaxation=1,
+                                                  dt=60.0, settings_kw=dict(coupling_minutes=60)), None),
+    ("time step 20 s, plain forecast with sky view", dict(npoints=2, hours=2, seed=51, dt=20.0, sky_view_fraction=1.0), None),
 ]
 
 
