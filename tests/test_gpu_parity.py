@@ -1274,3 +1274,12 @@ def test_other_time_steps_are_bit_identical_too(rslib, oracle):
         r, st_gpu, st_cpu, _, _ = _run_both(rslib, oracle, arrays, settings, params)
         _assert_parity(r)
         assert np.array_equal(st_gpu, st_cpu), dt
+
+
+def test_extreme_inputs_are_bit_identical_too(rslib, oracle):
+    """Storage caps and snow / ice transitions under heavy precipitation, a 40-degree surface, six places around
+    the globe on a leap day, the turn of the year (tests/extreme_cases.py; the two CPU restatements agree on them)."""
+    from extreme_cases import extreme_cases
+    for name, arrays, settings, params in extreme_cases():
+        r, st_gpu, st_cpu, _, _ = _run_both(rslib, oracle, arrays, settings, params)
+        assert r["bit_identical"] and np.array_equal(st_gpu, st_cpu), (name, r)

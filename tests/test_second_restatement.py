@@ -102,3 +102,25 @@ def test_two_restatements_agree_on_the_odd_paths(oracle, name, kw, post):
             d = np.abs(v - ref.out[k][p])
             assert not (np.nanmax(d) >= 1e-9), (name, p, k, int(np.nanargmax(d)), float(np.nanmax(d)))
     assert total == executed, name
+
+
+from extreme_cases import extreme_cases as _extreme_cases
+
+
+def test_two_restatements_agree_on_extreme_inputs(oracle):
+    for name, arrays, settings, params in _extreme_cases():
+        ref = arrays.copy()
+        st, executed = oracle.run_batch(ref, settings, params, nthreads=1)
+        total = 0
+        for p in range(arrays.npoints):
+            out, nsteps, failed = py_restatement.run_point(arrays, settings, params, p)
+            total += nsteps
+            assert failed == bool(st[p] & 1), (name, p)
+            for k, v in out.items():
+                assert np.array_equal(np.isnan(v), np.isnan(ref.out[k][p])), (name, p, k)
+                d = np.abs(v - ref.out[k][p])
+                assert not (np.nanmax(d) >= 1e-9), (name, p, k, int(np.nanargmax(d)), float(np.nanmax(d)))
+        assert total == executed, name
+        print(name, "max snow %.2f ice %.2f water %.2f Ts [%.1f, %.1f] failed %d" % (
+            ref.out["SnowOut"].max(), ref.out["IceOut"].max(), ref.out["WaterOut"].max(),
+            ref.out["TsurfOut"][ref.out["TsurfOut"] > -9000].min(), ref.out["TsurfOut"].max(), int((st & 1).sum())))
