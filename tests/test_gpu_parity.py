@@ -1283,3 +1283,25 @@ def test_extreme_inputs_are_bit_identical_too(rslib, oracle):
     for name, arrays, settings, params in extreme_cases():
         r, st_gpu, st_cpu, _, _ = _run_both(rslib, oracle, arrays, settings, params)
         assert r["bit_identical"] and np.array_equal(st_gpu, st_cpu), (name, r)
+
+
+def test_randomised_parameters_and_settings_fuzz(rslib, oracle):
+    """Twelve random configurations: every one of the 69 InputParameters scaled by a random factor in [0.8, 1.25]
+    (sign-preserving; the integer-valued hours and missing-value markers kept), random layer count, output depth,
+    coupling window and decay, relaxation on / off -- GPU against the oracle, bit for bit, status words included."""
+    rng = np.random.default_rng(20191207)
+    keep = {"NightOn", "NightOff", "MissValI", "MissValR"}
+    for trial in range(12):
+        base = abi.default_parameters(30.0)
+        over = {n: getattr(base, n) * rng.uniform(0.8, 1.25) for n, _ in base._fields_ if n not in keep}
+        params = abi.default_parameters(30.0, **over)
+        nl = int(rng.choice([15, 15, 6, 10, 24]))
+        coupled = bool(rng.integers(0, 2))
+        skw = dict(coupling_minutes=int(rng.choice([30, 60, 180])), coupling_effect_reduction=float(rng.choice([3600.0, 14400.0])))
+        if rng.integers(0, 3) == 0:
+            skw["tsurf_output_depth"] = float(rng.choice([0.0, 0.02, 0.3]))
+        arrays, settings, _, _ = synth.make_case(64, 4, seed=100 + trial, nlayers=nl, analysis_hours=4 if coupled else 0,
+                                                 use_coupling=int(coupled), use_relaxation=int(rng.integers(0, 2)) if coupled else 0,
+                                                 sky_view_fraction=float(rng.choice([0.0, 0.3, 1.0])), settings_kw=skw)
+        r, st_gpu, st_cpu, _, _ = _run_both(rslib, oracle, arrays, settings, params)
+        assert r["bit_identical"] and np.array_equal(st_gpu, st_cpu), (trial, nl, coupled, skw, r)
