@@ -1305,3 +1305,47 @@ def test_randomised_parameters_and_settings_fuzz(rslib, oracle):
                                                  sky_view_fraction=float(rng.choice([0.0, 0.3, 1.0])), settings_kw=skw)
         r, st_gpu, st_cpu, _, _ = _run_both(rslib, oracle, arrays, settings, params)
         assert r["bit_identical"] and np.array_equal(st_gpu, st_cpu), (trial, nl, coupled, skw, r)
+
+
+def test_irregular_record_grid_with_missing_records_inside(rslib, oracle):
+    """Coarse mode on an IRREGULAR record grid (gaps of 1 step to several hours, a record exactly on a model step and
+    in between) with records missing inside the series: optional variables (TSurfObs, PrecPhase, LW_net / SW_dir of
+    points without sky view) stay missing between their neighbours, a missing required value stops the point at the
+    first step that sees it -- the device-side interpolation against the oracle on host-interpolated arrays."""
+    import torch
+    arrays, settings, params, rec = synth.make_case(96, 12, seed=330, sky_view_fraction=0.5)
+    rng = np.random.default_rng(9)
+    # an irregular subset of model steps as record times: keep the hourly values but move the times
+    rs = np.unique(np.concatenate([[0, 1, 2, 121, 500, 501], rng.integers(3, arrays.sim_len + 200, size=rec.nrec - 8),
+                                   [arrays.sim_len + 300, arrays.sim_len + 301]])).astype(np.int32)[:rec.nrec]
+    assert len(rs) == rec.nrec and rs[-1] > arrays.sim_len - 1
+    irr = synth.Records(96, rec.nrec)
+    for v in synth.RECORD_VARS:
+        setattr(irr, v, getattr(rec, v).copy())
+    irr.lat, irr.lon, irr.sky_view, irr.horizons = rec.lat, rec.lon, rec.sky_view, rec.horizons
+    irr.record_step = rs
+    irr.TSurfObs[:, 3:] = -9999.9                       # observations only at the very start
+    irr.PrecPhase[::3, 4] = -9999                       # unknown phase for one record: interpretation from Tair
+    irr.tair[5, 6] = -9999.9                            # point 5: a required value missing inside the series
+    irr.LW[7, rec.nrec // 2] = -9999.9                  # point 7: likewise, later
+    fields = synth.interpolate_records(irr, arrays.sim_len)
+    ref = arrays.copy()
+    for name, val in fields.items():
+        getattr(ref, name)[...] = val
+    st_cpu, _ = oracle.run_batch(ref, settings, params, nthreads=4)
+    assert (st_cpu[[5, 7]] & rslib.ST_BAD_INPUT).all() and (np.delete(st_cpu, [5, 7]) & rslib.ST_FAILED == 0).all()
+    rslib.set_model(settings, params)
+    db = rslib.DeviceBatch(96, arrays.sim_len, n_records=irr.nrec, coarse=True, horizons=True)
+    db.load_records(irr)
+    db.time_fields.copy_(torch.from_numpy(arrays.time))
+    db.load_local(arrays.local, arrays.local_horizons)
+    db.run()
+    torch.cuda.synchronize()
+    got = db.outputs()
+    assert np.array_equal(db.status.cpu().numpy()[:96], st_cpu)
+    for k in ref.out:
+        same = (got[k] == ref.out[k]) | (np.isnan(got[k]) & np.isnan(ref.out[k]))
+        for p in (5, 7):                                # the one step executed on missing values (see the test above)
+            t = int(np.argmax(ref.out[k][p] == -9999.0)) - 1
+            same[p, t] |= np.isclose(got[k][p, t], ref.out[k][p, t], rtol=1e-6, atol=0.0, equal_nan=True)
+        assert same.all(), (k, np.argwhere(~same)[:5].tolist())
