@@ -374,11 +374,19 @@ def test_concurrent_runsimulation_calls_are_combined_into_batches(rslib):
     rslib.run_batch(r1, s1, p1)
     rslib.run_batch(r2, s2, p2)
     errors = []
+    import ctypes as C
+    L = rslib.load()
+    # the ctypes argument structs are built once: rebuilding them per call (rslib.runsimulation does) costs
+    # milliseconds under the GIL, staggers the ten threads by more than a batch takes, and the test would then
+    # measure Python, not the library's gathering of concurrent callers
+    ptrs = {id(a): (a.input_pointers(), a.output_pointers()) for a in (a1, a2)}
 
     def work(arrays, settings, params, pts):
         try:
+            ins, outs = ptrs[id(arrays)]
             for p in pts:
-                rslib.runsimulation(arrays, settings, params, point=p)
+                L.runsimulation(C.byref(outs[p]), C.byref(ins[p]), C.byref(settings), C.byref(params),
+                                C.byref(arrays.local[p]))
         except Exception as e:  # pragma: no cover
             errors.append(e)
     threads = [threading.Thread(target=work, args=(a1, s1, p1, range(k * 6, k * 6 + 6))) for k in range(8)]
