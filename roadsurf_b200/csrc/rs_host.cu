@@ -1766,6 +1766,11 @@ int roadsurf_set_option(const char* name, int value)
     g_opt_compaction = value > 0 ? (value > 30 ? 30 : value) : 0;
     return RS_OK;
   }
+  if (name && std::strcmp(name, "spread_small") == 0)
+  {
+    rs_set_spread_small(value);
+    return RS_OK;
+  }
   if (name && std::strcmp(name, "latency_body") == 0)
   {
     rs_set_latency_body(value);

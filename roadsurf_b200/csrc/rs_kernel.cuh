@@ -43,6 +43,10 @@ struct RsArgsCold
   int n_fixed;
   int mode;                      // RS_MODE_* bits
   int window_end;                // RS_MODE_SPLIT: the coupling window end every coupled point must have
+  int spread;                    // 0, or the number of points per warp (1, 2, 4, 8, 16; they sit in the first lanes,
+                                 // the other lanes are ghosts): small batches are latency-bound, and a warp that
+                                 // serves fewer points executes fewer sides of every branch (one point: 4.0 instead
+                                 // of 5.2 us per model step); set by rs_launch_run
   int tid0, tid_end;             // this launch covers the thread slots [tid0, tid_end) of the batch (0, 0 = all):
                                  // a large grid is launched as whole waves of 512-thread blocks + a tail of
                                  // 128-thread blocks spread over all SMs (see launch_sized)
@@ -70,6 +74,7 @@ int rs_launch_expand(const double* rec, const int* record_step, int n_records, i
 int rs_launch_partition(const double* flags_plane, int ld, int npoints, int sorted, int* index, int* n_index, void* stream);
 // `coupling`: the model has use_coupling set; `depth`: it has a fixed output depth (depth_mode != 0).  Both select
 // the kernel variant compiled with exactly the features the run needs.
+void rs_set_spread_small(int on);      // one point per warp for batches of at most 4 points per SM (default on)
 void rs_set_latency_body(int mode);  // -1 auto (small grids), 0 never, 1 every 128-thread launch
 int rs_launch_run(const RsArgs* a, const RsArgsCold* cold, int nlayers, int staged, int coupling, int relaxation, int depth,
                   void* stream, int* grid, int* block, int* regs, int* smem);

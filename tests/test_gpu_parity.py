@@ -1259,16 +1259,20 @@ def test_latency_body_and_throughput_body_give_identical_results(rslib, oracle):
     ref = arrays.copy()
     st_ref, _ = oracle.run_batch(ref, settings, params, nthreads=8)
     try:
-        for mode in (0, 1, -1):
-            rslib.set_option("latency_body", mode)
-            work = arrays.copy()
-            st = rslib.run_batch(work, settings, params)
-            assert np.array_equal(st, st_ref), mode
-            _assert_parity(compare(work.out, ref.out))
-            regs = rslib.last_launch()["regs_per_thread"]
-            assert (regs > 168) == (mode != 0), (mode, regs)      # the latency body has no register cap
+        for spread in (0, 1):       # one point per warp (the default for batches this small) or 32
+            rslib.set_option("spread_small", spread)
+            for mode in (0, 1, -1):
+                rslib.set_option("latency_body", mode)
+                work = arrays.copy()
+                st = rslib.run_batch(work, settings, params)
+                assert np.array_equal(st, st_ref), (spread, mode)
+                _assert_parity(compare(work.out, ref.out))
+                li = rslib.last_launch()
+                assert (li["regs_per_thread"] > 168) == (mode != 0), (mode, li)      # the latency body has no register cap
+                assert li["grid"] == (80 if spread else 3), li                       # 320 slots: 4 or 128 points per block
     finally:
         rslib.set_option("latency_body", -1)
+        rslib.set_option("spread_small", 1)
 
 
 def test_other_time_steps_are_bit_identical_too(rslib, oracle):
