@@ -522,6 +522,10 @@ void roadsurf_release_workspace(void);
  * memory, the saturation-pressure exponentials evaluated in the shadow of the boundary-layer divisions, no register
  * cap).  -1 = the latency body for grids of at most one 128-thread block per SM, 0 = never, 1 = for every launch of
  * 128-thread blocks.
+ * "spread_small" (default 1): batches of at most four points per SM run one point per warp (lane 0 owns the point,
+ * the other lanes follow as ghosts), larger ones up to 16 times that 2 .. 16 points per warp: a warp then executes
+ * only its own points' branches (4.0 instead of 5.2 us per model step for one point).  0 = always 32 points per
+ * warp; a value > 1 caps the points per warp.  Results are identical.
  * "max_points_per_device_batch": cap on the points roadsurf_run_batch puts into one device batch
  * (0 = bounded by free device memory only); batches beyond it are processed one after another. */
 int roadsurf_set_option(const char* name, int value);
