@@ -1361,3 +1361,15 @@ def test_irregular_record_grid_with_missing_records_inside(rslib, oracle):
             t = int(np.argmax(ref.out[k][p] == -9999.0)) - 1
             same[p, t] |= np.isclose(got[k][p, t], ref.out[k][p, t], rtol=1e-6, atol=0.0, equal_nan=True)
         assert same.all(), (k, np.argwhere(~same)[:5].tolist())
+
+
+def test_batch_sizes_across_the_points_per_warp_choices(rslib, oracle):
+    """rs_launch_run maps small batches to 1, 2, 4, 8 or 16 points per warp (the other lanes are ghosts) and larger
+    ones to 32: coupled batches whose sizes land in each of those choices -- and whose compacted coupling passes
+    therefore read their index lists through each mapping -- against the oracle, bit for bit."""
+    for npts in (31, 593, 1300, 2500, 5000, 9500, 20000):
+        arrays, settings, params, _ = synth.make_case(npts, 2, seed=500 + npts, analysis_hours=2, use_coupling=1,
+                                                       use_relaxation=1, settings_kw=dict(coupling_minutes=45))
+        r, st_gpu, st_cpu, _, _ = _run_both(rslib, oracle, arrays, settings, params)
+        assert r["bit_identical"] and np.array_equal(st_gpu, st_cpu), (npts, r)
+    assert (st_gpu & rslib.ST_COUPLING_USED).any()
