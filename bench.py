@@ -50,6 +50,9 @@ WORKLOADS = {
                name="c4: synthetic km-scale road grid, 24 h forecast, 10^7 points over 8 GPUs"),
     "c3": dict(total=100_000, per_gpu=100_000, hours=48, analysis=6, coupling=True,
                name="c3: synthetic national road network, 10^5 points, 6 h analysis + 48 h forecast, coupling + relaxation"),
+    "c2": dict(total=401, per_gpu=401, hours=26, analysis=48, coupling=True,
+               name="c2: example1's shape, 401 stations, 48 h analysis + 26 h forecast, coupling + relaxation "
+                    "(latency-bound: a warp per point)"),
     "c5": dict(total=51_000_000, per_gpu=6_375_000, hours=48, analysis=0, coupling=False,
                name="c5: 51-member ensemble x 10^6 points (flattened member x point), 48 h forecast"),
 }
