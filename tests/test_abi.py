@@ -171,3 +171,23 @@ def test_new_entry_points_fail_loudly_without_a_gpu_and_validate_arguments():
         lib.prepare_statics(local, None, ngpus=1)
     # a stale / foreign handle is rejected, not dereferenced blindly
     assert handle.roadsurf_session_done(None) < 0
+
+
+def test_every_run_time_option_is_documented_in_the_header():
+    """roadsurf_set_option: every name the library accepts is described in include/roadsurf_b200.h, and an
+    unknown name is rejected (host only)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "roadsurf_b200", "csrc", "rs_host.cu")).read()
+    body = src[src.index("int roadsurf_set_option("):]
+    body = body[:body.index("\n}\n")]
+    names = re.findall(r'strcmp\(name, "([a-z_0-9]+)"\)', body)
+    assert len(names) >= 6, names
+    header = open(os.path.join(root, "include", "roadsurf_b200.h")).read()
+    for n in names:
+        assert '"%s"' % n in header, n
+    from roadsurf_b200 import lib
+    import pytest
+    with pytest.raises(Exception):
+        lib.set_option("no_such_option", 1)
